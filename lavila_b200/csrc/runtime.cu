@@ -1,0 +1,88 @@
+// Library runtime: error reporting, launch accounting, device queries, TMA descriptor encoding.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <mutex>
+
+#include "../../include/lavila_b200.h"
+#include "host_common.h"
+
+namespace lv {
+
+static thread_local char g_err[512] = "";
+static std::atomic<int64_t> g_launches{0};
+
+int set_error(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+int check_launch(const char* what) {
+  count_launch(1);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error((int)e, "%s: %s", what, cudaGetErrorString(e));
+  return 0;
+}
+
+int sm_count() {
+  static int cached[64];
+  static std::once_flag once[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  std::call_once(once[dev], [dev]() {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached[dev] = n;
+  });
+  return cached[dev];
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, []() {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t inner, uint64_t rows, uint64_t ld,
+                      uint32_t box_inner, uint32_t box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return set_error(-2, "cuTensorMapEncodeTiled not available (no CUDA driver?)");
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || ((ld * 2) & 15))
+    return set_error(-1, "TMA operand must be 16-byte aligned with a 16-byte-multiple row pitch (ld=%llu)",
+                     (unsigned long long)ld);
+  cuuint64_t dims[2] = {inner, rows};
+  cuuint64_t strides[1] = {ld * 2};
+  cuuint32_t box[2] = {box_inner, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return set_error(-3, "cuTensorMapEncodeTiled failed (%d) inner=%llu rows=%llu ld=%llu box=%ux%u", (int)r,
+                     (unsigned long long)inner, (unsigned long long)rows, (unsigned long long)ld, box_inner, box_rows);
+  return 0;
+}
+
+}  // namespace lv
+
+extern "C" {
+int lv_version(void) { return LV_ABI_VERSION; }
+const char* lv_last_error(void) { return lv::g_err; }
+int64_t lv_launch_count(void) { return lv::g_launches.load(); }
+}
