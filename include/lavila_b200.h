@@ -73,6 +73,90 @@ typedef struct LvGemmEpilogue {
 int lv_gemm_bf16(const void* A, int64_t lda, int a_mn, const void* B, int64_t ldb, int b_mn, int64_t M, int64_t N,
                  int64_t K, int k_splits, const LvGemmEpilogue* epi, void* stream);
 
+
+/* ------------------------------------------------------------------------------------------------
+ * LayerNorm over the last dimension (one warp per row, fp32 statistics).  D % 128 == 0, D <= 1024.
+ * Replaces nn.LayerNorm at lavila/models/timesformer.py:180,189,196 (eps 1e-6), :366 ln_pre (1e-5), :377 norm;
+ * lavila/models/openai_model.py:196,200 ln_1/ln_2 and models.py:156 ln_final (1e-5).
+ *   fwd: y = LN(x) written as bf16 (GEMM operand) and/or fp32.  Any of y_bf16 / y_f32 may be NULL (not both).
+ *   bwd: dx = dLN(dy) [+ add1] [+ add2] written as fp32 and/or bf16; dgamma/dbeta accumulated with fp32 atomics
+ *        (may be NULL together).  mean/rstd are recomputed from x.
+ * ---------------------------------------------------------------------------------------------- */
+int lv_layernorm_fwd(const float* x, int64_t ldx, const float* gamma, const float* beta, float eps, void* y_bf16,
+                     int64_t ldy, float* y_f32, int64_t ldyf, int64_t rows, int D, void* stream);
+int lv_layernorm_bwd(const void* dy, int dy_is_bf16, int64_t lddy, const float* x, int64_t ldx, const float* gamma,
+                     float eps, const float* add1, int64_t ld1, const float* add2, int64_t ld2, float* dx, int64_t lddx,
+                     void* dx_bf16, int64_t lddxb, float* dgamma, float* dbeta, int64_t rows, int D, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Divided space-time attention + causal text attention (head_dim 64), in place on the packed projection output.
+ * Replaces VarAttention.forward's regroup/concat/bmm/softmax/bmm chain, lavila/models/timesformer.py:111-140 and
+ * attn() :35-39; nn.MultiheadAttention's core at lavila/models/openai_model.py:196-198 (mode 2).
+ *   qkv  bf16 [rows, 3*D] = [q | k | v] (D = H*64), out bf16 [rows, D], lse fp32 [rows, H].
+ *   mode 0 = space  (group = (clip, head, frame):      n queries, n + CLS keys)
+ *   mode 1 = time   (group = (clip, head, position):   T queries, T + CLS keys, token stride n)
+ *   mode 2 = causal (group = (caption, head):          L queries/keys, additive -inf upper triangle)
+ *   rows = B * (1 + T*n) for modes 0/1 (token 0 of each clip is CLS), B * L for mode 2.
+ * The group kernels write the patch-token rows; lv_cls_attn_* handle token 0 (the CLS query attends to all N tokens,
+ * timesformer.py:119).  Backward call order for modes 0/1: lv_cls_attn_bwd -> lv_group_attn_bwd(accumulate_kv=1)
+ * -> lv_cls_kv_finalize.  dcls_kv: fp32 [B, H, 2, 64] scratch (written by lv_cls_attn_bwd, accumulated by the group
+ * kernel, consumed by finalize).
+ * ---------------------------------------------------------------------------------------------- */
+int lv_group_attn_fwd(const void* qkv, int64_t ld_qkv, void* out, int64_t ld_out, float* lse, int mode, int B, int H,
+                      int T, int n, int L, void* stream);
+int lv_group_attn_bwd(const void* qkv, int64_t ld_qkv, const void* out, int64_t ld_out, const float* lse,
+                      const void* dout, int64_t ld_dout, void* dqkv, int64_t ld_dqkv, float* dcls_kv, int accumulate_kv,
+                      int mode, int B, int H, int T, int n, int L, void* stream);
+int lv_cls_attn_fwd(const void* qkv, int64_t ld_qkv, void* out, int64_t ld_out, float* lse, int B, int H, int N,
+                    void* stream);
+int lv_cls_attn_bwd(const void* qkv, int64_t ld_qkv, const void* out, int64_t ld_out, const void* dout, int64_t ld_dout,
+                    const float* lse, void* dqkv, int64_t ld_dqkv, float* dcls_kv, int B, int H, int N, void* stream);
+int lv_cls_kv_finalize(const float* dcls_kv, void* dqkv, int64_t ld_dqkv, int B, int H, int N, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * HBM-bound glue (elementwise.cu)
+ * ---------------------------------------------------------------------------------------------- */
+/* fp32 -> bf16 (weights each step; autocast's implicit casts in the reference). */
+int lv_cast_f32_bf16(const float* in, void* out, int64_t n, void* stream);
+/* out[n] += sum_m in[m,n] -- bias gradients (autograd of nn.Linear bias).  in bf16 [M,N]. */
+int lv_colsum_bf16(const void* in, int64_t ld, int64_t M, int N, float* out, void* stream);
+/* frames fp32 [B,C,T,H,W] -> patch matrix bf16 [B*T*(H/P)*(W/P), ldp], column (c*P+py)*P+px.
+ * Folds timesformer.py:387 permute+contiguous and the Conv2d(k=P,s=P) input gather (:77,:82-83). */
+int lv_patch_im2col(const float* frames, void* patches, int B, int C, int T, int H, int W, int P, int64_t ldp,
+                    void* stream);
+/* x0[b,0] = cls + pos[0]; x0[b,1+f*n+i] = patch[(b*T+f)*n+i] + pos[1+i] + temporal[f]  (timesformer.py:353-364). */
+int lv_embed_assemble(const float* patch, const float* cls, const float* pos, const float* temporal, float* x0, int B,
+                      int T, int n, int D, void* stream);
+/* Gradients of the above: dpos/dcls/dtemporal accumulated (+=), dpatch written as compact bf16 [B*T*n, D]. */
+int lv_embed_assemble_bwd(const float* dx0, float* dpos, float* dcls, float* dtemporal, void* dpatch_bf16, int B, int T,
+                          int n, int D, void* stream);
+/* x[r] = tok[text[r]] + pos[r % L]  (models.py:151-152) and its gradient (fp32 atomics). text is int64. */
+int lv_text_embed(const int64_t* text, const float* tok, const float* pos, float* x, int64_t rows, int L, int W, int vocab,
+                  void* stream);
+int lv_text_embed_bwd(const int64_t* text, const float* dx, float* dtok, float* dpos, int64_t rows, int L, int W,
+                      int vocab, void* stream);
+/* argmax over the last dim of int64 [B,L], first maximum (models.py:160 EOT pick) -- bit exact. */
+int lv_argmax_i64(const int64_t* text, int32_t* out, int B, int L, void* stream);
+/* scatter=0: dst[r] = src[r*rows_per + idx[r]];  scatter=1: dst[r*rows_per + idx[r]] = src[r].  fp32 rows of W. */
+int lv_gather_rows_f32(const float* src, const int32_t* idx, float* dst, int R, int rows_per, int W, int scatter,
+                       void* stream);
+/* F.normalize(dim=-1) (models.py:169-170) and its gradient. */
+int lv_l2norm_fwd(const float* x, float* y, float* norm, int R, int E, void* stream);
+int lv_l2norm_bwd(const float* dy, const float* y, const float* norm, float* dx, int R, int E, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * CLIPLoss on the gathered global batch (lavila/models/loss.py:76-79,107-116).
+ *   fwd: result[0] = loss, result[1] = clip_acc (%).  lse_img/lse_txt [Ng], partial [2*Ng], counter (zeroed once).
+ *   bwd: gradients of the LOCAL rows [r0, r0+Nl) only, multiplied by grad_scale (= world size for the
+ *        --contrastive-use-vissl path, distributed_utils.py:64-67, where the reference all_reduce-SUMs identical
+ *        per-rank gradients); d_scale (may be NULL) accumulates scale_grad_scale * sum over local image rows.
+ * ---------------------------------------------------------------------------------------------- */
+int lv_clip_loss_fwd(const float* img, const float* txt, const float* scale_ptr, int Ng, int E, float* lse_img,
+                     float* lse_txt, float* partial, uint32_t* counter, float* result, void* stream);
+int lv_clip_loss_bwd(const float* img, const float* txt, const float* scale_ptr, const float* lse_img,
+                     const float* lse_txt, const float* gout, float grad_scale, float scale_grad_scale, int Ng, int E,
+                     int r0, int Nl, float* d_img, float* d_txt, float* d_scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,228 @@
+// CLIPLoss forward/backward on the (gathered) global batch -- lavila/models/loss.py:76-79,107-116.
+//
+//   logits[i,j] = s * <I_i, T_j>,  loss = (CE(logits, arange) + CE(logits^T, arange)) / 2,  acc = 100 * mean(argmax_j == i)
+//
+// Ng <= 8 * per-GPU batch (512 at 8 GPUs), E = 256: 134 MFLOP -- latency-bound, so ONE kernel does logits, both
+// log-sum-exps, the label pick, the arg-max and the mean (last-CTA-done reduction), and one kernel produces the
+// gradients of the LOCAL rows only.  Every rank evaluates the same global loss, so the reference's backward
+// all_reduce(SUM) of identical per-rank gradients (distributed_utils.py:64-67) is just a factor W: it is applied as
+// `grad_scale` and the collective disappears from the backward pass.
+// fp32 throughout (the reference's autocast runs the matmul in bf16 and CE in fp32; fp32 is >= that precision).
+#include "../../include/lavila_b200.h"
+#include "host_common.h"
+#include "ptx.cuh"
+
+namespace lv {
+namespace loss {
+
+constexpr int THREADS = 256;
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// dot(a_row (smem), B[j,:]) for all j handled by this thread
+__device__ __forceinline__ float dot_row(const float* __restrict__ a_s, const float* __restrict__ b, int E) {
+  float acc = 0.f;
+  for (int c = 0; c < E; c += 4) {
+    const float4 x = *reinterpret_cast<const float4*>(a_s + c);
+    const float4 y = __ldg(reinterpret_cast<const float4*>(b + c));
+    acc += x.x * y.x + x.y * y.y + x.z * y.z + x.w * y.w;
+  }
+  return acc;
+}
+
+// block-wide (max, argmax-first, sum-exp) over values v[j], j = tid + k*THREADS
+struct RowStat { float lse; int argmax; float label_logit; };
+
+__device__ RowStat row_stats(const float* vals, int Ng, int label, float* sred, int* ired) {
+  // vals in shared memory [Ng]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float m = -INFINITY;
+  int am = 0x7fffffff;
+  for (int j = tid; j < Ng; j += THREADS) {
+    const float v = vals[j];
+    if (v > m) { m = v; am = j; }
+  }
+  // warp arg-max with first-index tie-break
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float om = __shfl_xor_sync(0xffffffffu, m, o);
+    const int oa = __shfl_xor_sync(0xffffffffu, am, o);
+    if (om > m || (om == m && oa < am)) { m = om; am = oa; }
+  }
+  if (lane == 0) { sred[warp] = m; ired[warp] = am; }
+  __syncthreads();
+  float bm = sred[0];
+  int ba = ired[0];
+  for (int w = 1; w < THREADS / 32; ++w) {
+    const float om = sred[w];
+    const int oa = ired[w];
+    if (om > bm || (om == bm && oa < ba)) { bm = om; ba = oa; }
+  }
+  __syncthreads();
+  float s = 0.f;
+  for (int j = tid; j < Ng; j += THREADS) s += __expf(vals[j] - bm);
+  s = warp_sum(s);
+  if (lane == 0) sred[warp] = s;
+  __syncthreads();
+  float tot = 0.f;
+  for (int w = 0; w < THREADS / 32; ++w) tot += sred[w];
+  __syncthreads();
+  RowStat r;
+  r.lse = bm + logf(tot);
+  r.argmax = ba;
+  r.label_logit = vals[label];
+  return r;
+}
+
+// grid = Ng CTAs; CTA i handles image row i and text row i.
+// out: lse_img[Ng], lse_txt[Ng], result[3] = {loss, acc(%), scratch}, counter for the last-CTA reduction.
+__global__ void __launch_bounds__(THREADS)
+clip_loss_fwd_kernel(const float* __restrict__ img, const float* __restrict__ txt, const float* __restrict__ scale_ptr,
+                     int Ng, int E, float* __restrict__ lse_img, float* __restrict__ lse_txt,
+                     float* __restrict__ partial /*[Ng][2]*/, unsigned int* __restrict__ counter,
+                     float* __restrict__ result) {
+  extern __shared__ float sm[];
+  float* a_img = sm;            // [E]
+  float* a_txt = sm + E;        // [E]
+  float* vals = sm + 2 * E;     // [Ng]
+  __shared__ float sred[THREADS / 32];
+  __shared__ int ired[THREADS / 32];
+  __shared__ bool is_last;
+  const int i = blockIdx.x, tid = threadIdx.x;
+  const float s = __ldg(scale_ptr);
+  for (int c = tid; c < E; c += THREADS) {
+    a_img[c] = s * img[(long long)i * E + c];   // (logit_scale * I) @ T^T : scale applied to the image row first
+    a_txt[c] = txt[(long long)i * E + c];
+  }
+  __syncthreads();
+  // image -> text logits, row i
+  for (int j = tid; j < Ng; j += THREADS) vals[j] = dot_row(a_img, txt + (long long)j * E, E);
+  __syncthreads();
+  const RowStat ri = row_stats(vals, Ng, i, sred, ired);
+  __syncthreads();
+  // text -> image logits, row i of logits^T : s * <I_j, T_i>
+  for (int j = tid; j < Ng; j += THREADS) vals[j] = s * dot_row(a_txt, img + (long long)j * E, E);
+  __syncthreads();
+  const RowStat rt = row_stats(vals, Ng, i, sred, ired);
+  if (tid == 0) {
+    lse_img[i] = ri.lse;
+    lse_txt[i] = rt.lse;
+    partial[2 * i] = 0.5f * ((ri.lse - ri.label_logit) + (rt.lse - rt.label_logit));
+    partial[2 * i + 1] = (ri.argmax == i) ? 1.f : 0.f;
+    __threadfence();
+    const unsigned int done = atomicAdd(counter, 1u);
+    is_last = (done == (unsigned)Ng - 1);
+  }
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    float l = 0.f, a = 0.f;
+    for (int j = tid; j < Ng; j += THREADS) {
+      l += __ldcg(partial + 2 * j);
+      a += __ldcg(partial + 2 * j + 1);
+    }
+    l = warp_sum(l);
+    a = warp_sum(a);
+    __shared__ float lr[THREADS / 32], ar[THREADS / 32];
+    if ((tid & 31) == 0) { lr[tid >> 5] = l; ar[tid >> 5] = a; }
+    __syncthreads();
+    if (tid == 0) {
+      float L = 0.f, A = 0.f;
+      for (int w = 0; w < THREADS / 32; ++w) { L += lr[w]; A += ar[w]; }
+      result[0] = L / Ng;
+      result[1] = 100.f * A / Ng;
+      *counter = 0;  // self-reset for the next call
+    }
+  }
+}
+
+// grid = 2 * Nl CTAs (Nl local rows starting at global row r0).  CTA k < Nl: d loss / d I_{r0+k};  k >= Nl: d loss / d T_{r0+k-Nl}.
+//   dlogits[i,j] = ( softmax_img[i,j] + softmax_txt[j,i] - 2*delta_ij ) / (2 Ng)
+//   dI_i = g * s * sum_j dlogits[i,j] T_j        dT_j = g * s * sum_i dlogits[i,j] I_i
+//   dscale += g0 * sum_{i local, j} dlogits[i,j] <I_i,T_j>   (each rank contributes its local rows; callers sum / DDP averages)
+// g = upstream grad * grad_scale (W for the vissl path).
+__global__ void __launch_bounds__(THREADS)
+clip_loss_bwd_kernel(const float* __restrict__ img, const float* __restrict__ txt, const float* __restrict__ scale_ptr,
+                     const float* __restrict__ lse_img, const float* __restrict__ lse_txt,
+                     const float* __restrict__ gout_ptr, float grad_scale, float scale_grad_scale, int Ng, int E, int r0,
+                     int Nl, float* __restrict__ d_img, float* __restrict__ d_txt, float* __restrict__ d_scale) {
+  extern __shared__ float sm[];
+  float* a_row = sm;          // [E] the row this CTA differentiates
+  float* w = sm + E;          // [Ng] dlogits coefficients
+  __shared__ float sred[THREADS / 32];
+  const int tid = threadIdx.x;
+  const bool is_img = blockIdx.x < (unsigned)Nl;
+  const int i = r0 + (is_img ? blockIdx.x : blockIdx.x - Nl);
+  const float s = __ldg(scale_ptr);
+  const float gout = __ldg(gout_ptr);
+  const float* self = is_img ? img : txt;
+  const float* other = is_img ? txt : img;
+  for (int c = tid; c < E; c += THREADS) a_row[c] = self[(long long)i * E + c];
+  __syncthreads();
+  const float my_lse_img = is_img ? lse_img[i] : 0.f;
+  const float my_lse_txt = is_img ? 0.f : lse_txt[i];
+  float ds = 0.f;
+  for (int j = tid; j < Ng; j += THREADS) {
+    const float l = s * dot_row(a_row, other + (long long)j * E, E);   // logits[i,j] (img CTA) or logits[j,i] (txt CTA)
+    float p_img, p_txt;
+    if (is_img) { p_img = __expf(l - my_lse_img); p_txt = __expf(l - lse_txt[j]); }
+    else        { p_img = __expf(l - lse_img[j]); p_txt = __expf(l - my_lse_txt); }
+    const float d = (p_img + p_txt - ((j == i) ? 2.f : 0.f)) / (2.f * Ng);
+    w[j] = d;
+    ds += d * l;
+  }
+  __syncthreads();
+  // d(row) = g * s * sum_j w[j] * other[j,:]
+  float* dst = (is_img ? d_img : d_txt) + (long long)(i - r0) * E;
+  for (int c = tid; c < E; c += THREADS) {
+    float acc = 0.f;
+    for (int j = 0; j < Ng; ++j) acc += w[j] * __ldg(other + (long long)j * E + c);
+    dst[c] = gout * grad_scale * s * acc;
+  }
+  if (is_img && d_scale) {
+    ds = warp_sum(ds);
+    if ((tid & 31) == 0) sred[tid >> 5] = ds;
+    __syncthreads();
+    if (tid == 0) {
+      float t = 0.f;
+      for (int k = 0; k < THREADS / 32; ++k) t += sred[k];
+      // ds accumulated d * l = d * s * <I,T>;  d loss / d s = sum d * <I,T> = t / s
+      atomicAdd(d_scale, gout * scale_grad_scale * t / s);
+    }
+  }
+}
+
+}  // namespace loss
+}  // namespace lv
+
+using namespace lv;
+
+extern "C" int lv_clip_loss_fwd(const float* img, const float* txt, const float* scale_ptr, int Ng, int E, float* lse_img,
+                                float* lse_txt, float* partial, uint32_t* counter, float* result, void* stream) {
+  LV_REQUIRE(img && txt && scale_ptr && lse_img && lse_txt && partial && counter && result, "lv_clip_loss_fwd: null pointer");
+  LV_REQUIRE(Ng > 0 && E > 0 && E % 4 == 0, "lv_clip_loss_fwd: bad shape Ng=%d E=%d", Ng, E);
+  const size_t smem = (size_t)(2 * E + Ng) * sizeof(float);
+  LV_REQUIRE(smem <= 48 * 1024, "lv_clip_loss_fwd: Ng=%d too large for one CTA row buffer", Ng);
+  loss::clip_loss_fwd_kernel<<<Ng, loss::THREADS, smem, (cudaStream_t)stream>>>(img, txt, scale_ptr, Ng, E, lse_img, lse_txt, partial, counter, result);
+  return check_launch("lv_clip_loss_fwd");
+}
+
+extern "C" int lv_clip_loss_bwd(const float* img, const float* txt, const float* scale_ptr, const float* lse_img,
+                                const float* lse_txt, const float* gout, float grad_scale, float scale_grad_scale, int Ng,
+                                int E, int r0, int Nl, float* d_img, float* d_txt, float* d_scale, void* stream) {
+  LV_REQUIRE(img && txt && scale_ptr && lse_img && lse_txt && gout && d_img && d_txt, "lv_clip_loss_bwd: null pointer");
+  LV_REQUIRE(Ng > 0 && E % 4 == 0 && r0 >= 0 && Nl > 0 && r0 + Nl <= Ng, "lv_clip_loss_bwd: bad shape");
+  const size_t smem = (size_t)(E + Ng) * sizeof(float);
+  LV_REQUIRE(smem <= 48 * 1024, "lv_clip_loss_bwd: Ng too large");
+  loss::clip_loss_bwd_kernel<<<2 * Nl, loss::THREADS, smem, (cudaStream_t)stream>>>(img, txt, scale_ptr, lse_img, lse_txt, gout, grad_scale, scale_grad_scale, Ng, E, r0, Nl, d_img, d_txt, d_scale);
+  return check_launch("lv_clip_loss_bwd");
+}

@@ -2,10 +2,10 @@
 //
 //   C[M,N] = epilogue( A_op[M,K] * B_op[N,K]^T ),  fp32 accumulation in TMEM.
 //
-// One CTA per SM, 192 threads:
+// One CTA per SM, 320 threads:
 //   warp 0      : TMA producer   (cp.async.bulk.tensor -> 128B-swizzled smem ring, 4 stages x 48 KB)
 //   warp 1      : MMA issuer     (one lane issues tcgen05.mma 128x256x16; tcgen05.commit frees smem stages)
-//   warps 2..5  : epilogue       (tcgen05.ld -> registers -> smem transpose -> fused, coalesced global I/O)
+//   warps 2..9  : epilogue       (tcgen05.ld -> registers -> smem transpose -> fused, coalesced 128-bit global I/O)
 // The 512 TMEM columns hold two 128x256 fp32 accumulators, so the epilogue of tile i overlaps the MMAs of
 // tile i+1.  Operands may be K-major (row-major [rows][K]) or MN-major ([K][rows], e.g. activations in a weight
 // gradient), which lets forward, dgrad and wgrad all read the tensors PyTorch already holds, with no transposes.
@@ -30,12 +30,13 @@ constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB
 constexpr int B_STAGE_BYTES = BN * BK * 2;  // 32 KB
 constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
 constexpr int ATOM_BYTES = 64 * BK * 2;  // one 64(MN) x 64(K) MN-major sub-tile = 8 KB
-constexpr int EPI_PITCH = 33;
-constexpr int EPI_WARPS = 4;
+constexpr int EPI_PITCH = 16;  // floats: a 32-row x 16-column half chunk per warp, 16-byte units XOR-swizzled
+constexpr int EPI_WARPS = 8;  // two warps per TMEM lane quarter, each owning half of the 256 columns
 constexpr int EPI_BYTES = EPI_WARPS * 32 * EPI_PITCH * 4;
 constexpr int NUM_BARS = 2 * STAGES + 4;
 constexpr int SMEM_BYTES = 1024 /*alignment slack*/ + STAGES * STAGE_BYTES + EPI_BYTES + NUM_BARS * 8 + 16;
-constexpr int NUM_THREADS = 192;
+static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS;
 constexpr int TMEM_COLS = 512;
 
 struct Args {
@@ -54,13 +55,31 @@ struct Args {
   const float* scale_ptr;
 };
 
-__device__ __forceinline__ float sigmoidf_fast(float x) { return 1.0f / (1.0f + __expf(-x)); }
+// sigmoid(x) = 0.5 * tanh(0.5 x) + 0.5 : one SFU op (tanh.approx.f32, rel. error ~2^-11) instead of ex2 + rcp.
+// The GELU epilogues are SFU-bound otherwise (128x256 outputs x 2 MUFU / 16 per clk = 4096 cycles per tile).
+__device__ __forceinline__ float sigmoidf_fast(float x) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x));
+  return fmaf(0.5f, t, 0.5f);
+}
 
-template <int A_MN, int B_MN>
+// Flag sets with a dedicated compile-time specialisation (everything else runs the runtime-flag kernel).
+__host__ __device__ constexpr bool is_specialised(int a_mn, int b_mn, int f) {
+  if (!a_mn && !b_mn)
+    return f == 0 || f == LV_EPI_BIAS || f == (LV_EPI_BIAS | LV_EPI_QUICKGELU) || f == LV_EPI_OUT_F32 ||
+           f == (LV_EPI_BIAS | LV_EPI_RESID | LV_EPI_OUT_F32) ||
+           f == (LV_EPI_BIAS | LV_EPI_SCALE | LV_EPI_SCALE_TANH | LV_EPI_RESID | LV_EPI_OUT_F32);
+  if (!a_mn && b_mn) return f == 0 || f == LV_EPI_DQUICKGELU || f == LV_EPI_OUT_F32;
+  if (a_mn && b_mn) return f == (LV_EPI_ATOMIC | LV_EPI_OUT_F32);
+  return false;
+}
+
+template <int A_MN, int B_MN, int CT_FLAGS>  // CT_FLAGS < 0: epilogue flags are read at run time
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Args g) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // align by OFFSET arithmetic on the shared array so the compiler keeps the shared address space (LDS/STS)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * A_STAGE_BYTES;
   float* sEpi = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);
@@ -170,16 +189,18 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else {
     // ------------------------------------------------------------------ epilogue warps
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
-    float* buf = sEpi + (warp - 2) * 32 * EPI_PITCH;
-    const int flags = g.flags;
+    const int q = warp & 3;        // TMEM lane quarter this warp may access
+    const int e = warp - 2;        // 0..7
+    const int half = e >> 2;       // which 128 of the 256 accumulator columns
+    float* buf = sEpi + e * 32 * EPI_PITCH;
+    const int flags = CT_FLAGS >= 0 ? CT_FLAGS : g.flags;
     float scale = 1.0f;
     if (flags & LV_EPI_SCALE) {
       scale = __ldg(g.scale_ptr);
       if (flags & LV_EPI_SCALE_TANH) scale = tanhf(scale);
     }
-    const int row_l_base = lane >> 4;
-    const int col_l = 2 * (lane & 15);
+    const int r8 = lane >> 2;        // row within a group of 8
+    const int ch = lane & 3;         // this lane's 16-byte unit (4 columns) inside a 16-column half chunk
     int it = 0;
     for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++it) {
       const int split = item / n_tiles;
@@ -190,67 +211,93 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const uint32_t aphase = (it >> 1) & 1;
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
-      const int m0 = m_blk * BM + q * 32;
+      const int m_base = m_blk * BM + q * 32;
       const int n0 = n_blk * BN;
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int cc = 0; cc < BN / 64; ++cc) {
+        const int c = half * (BN / 64) + cc;
         if (n0 + c * 32 >= g.N) break;
+        // prefetch the epilogue's global operands for the whole 32x32 chunk (memory-level parallelism)
+        float4 pre_res[2][4];
+        uint2 pre_aux[2][4];
+        if (flags & (LV_EPI_RESID | LV_EPI_DQUICKGELU)) {
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            const int n = n0 + c * 32 + hh * 16 + ch * 4;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int m = m_base + 8 * i + r8;
+              if (m < g.M && n < g.N) {
+                if (flags & LV_EPI_RESID) pre_res[hh][i] = __ldg(reinterpret_cast<const float4*>(g.resid + (long long)m * g.ldr + n));
+                if (flags & LV_EPI_DQUICKGELU) pre_aux[hh][i] = __ldg(reinterpret_cast<const uint2*>(g.aux + (long long)m * g.ldaux + n));
+              }
+            }
+          }
+        }
         uint32_t r[32];
         tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + as * BN + c * 32, r);
         tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) buf[lane * EPI_PITCH + j] = __uint_as_float(r[j]);
-        __syncwarp();
-        const int n = n0 + c * 32 + col_l;
-        float b0 = 0.f, b1 = 0.f;
-        if ((flags & LV_EPI_BIAS) && !(flags & LV_EPI_ROWBIAS) && n < g.N) {
-          b0 = __ldg(g.bias + n);
-          b1 = __ldg(g.bias + n + 1);
-        }
-#pragma unroll 4
-        for (int i = 0; i < 16; ++i) {
-          const int row_l = 2 * i + row_l_base;
-          const int m = m0 + row_l;
-          float v0 = buf[row_l * EPI_PITCH + col_l];
-          float v1 = buf[row_l * EPI_PITCH + col_l + 1];
-          if (m < g.M && n < g.N) {
-            if (flags & LV_EPI_ROWBIAS) { b0 = b1 = __ldg(g.bias + m); }
-            v0 += b0;
-            v1 += b1;
-            if (flags & LV_EPI_QUICKGELU) {
-              const uint32_t hb = pack_bf16x2(v0, v1);
-              *reinterpret_cast<uint32_t*>(reinterpret_cast<__nv_bfloat16*>(g.out2) + (long long)m * g.ldo2 + n) = hb;
-              const float2 h = unpack_bf16x2(hb);
-              v0 = h.x * sigmoidf_fast(1.702f * h.x);
-              v1 = h.y * sigmoidf_fast(1.702f * h.y);
-            }
-            if (flags & LV_EPI_DQUICKGELU) {
-              const float2 h = unpack_bf16x2(__ldg(reinterpret_cast<const uint32_t*>(g.aux + (long long)m * g.ldaux + n)));
-              const float s0 = sigmoidf_fast(1.702f * h.x), s1 = sigmoidf_fast(1.702f * h.y);
-              v0 *= s0 * (1.0f + 1.702f * h.x * (1.0f - s0));
-              v1 *= s1 * (1.0f + 1.702f * h.y * (1.0f - s1));
-            }
-            if (flags & LV_EPI_SCALE) { v0 *= scale; v1 *= scale; }
-            if (flags & LV_EPI_RESID) {
-              const float2 rr = __ldg(reinterpret_cast<const float2*>(g.resid + (long long)m * g.ldr + n));
-              v0 += rr.x;
-              v1 += rr.y;
-            }
-            if (flags & LV_EPI_ATOMIC) {
-              float* o = reinterpret_cast<float*>(g.out) + (long long)m * g.ldo + n;
-              red_add_f32(o, v0);
-              red_add_f32(o + 1, v1);
-            } else if (flags & LV_EPI_OUT_F32) {
-              *reinterpret_cast<float2*>(reinterpret_cast<float*>(g.out) + (long long)m * g.ldo + n) = make_float2(v0, v1);
-            } else {
-              *reinterpret_cast<uint32_t*>(reinterpret_cast<__nv_bfloat16*>(g.out) + (long long)m * g.ldo + n) = pack_bf16x2(v0, v1);
-            }
-            if (flags & LV_EPI_COPY_BF16) {
-              *reinterpret_cast<uint32_t*>(reinterpret_cast<__nv_bfloat16*>(g.out2) + (long long)m * g.ldo2 + n) = pack_bf16x2(v0, v1);
+        for (int hh = 0; hh < 2; ++hh) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            *reinterpret_cast<float4*>(buf + lane * EPI_PITCH + ((j ^ ((lane >> 1) & 3)) << 2)) =
+                make_float4(__uint_as_float(r[hh * 16 + 4 * j]), __uint_as_float(r[hh * 16 + 4 * j + 1]),
+                            __uint_as_float(r[hh * 16 + 4 * j + 2]), __uint_as_float(r[hh * 16 + 4 * j + 3]));
+          __syncwarp();
+          const int n = n0 + c * 32 + hh * 16 + ch * 4;
+          const bool n_ok = n < g.N;
+          float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+          if ((flags & LV_EPI_BIAS) && !(flags & LV_EPI_ROWBIAS) && n_ok) bv = __ldg(reinterpret_cast<const float4*>(g.bias + n));
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int row_l = 8 * i + r8;
+            const int m = m_base + row_l;
+            float4 v = *reinterpret_cast<const float4*>(buf + row_l * EPI_PITCH + ((ch ^ ((row_l >> 1) & 3)) << 2));
+            if (m < g.M && n_ok) {
+              if (flags & LV_EPI_ROWBIAS) { const float b = __ldg(g.bias + m); bv = make_float4(b, b, b, b); }
+              if (flags & LV_EPI_BIAS) { v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w; }
+              if (flags & LV_EPI_QUICKGELU) {
+                uint2 hb = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+                *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(g.out2) + (long long)m * g.ldo2 + n) = hb;
+                const float2 h0 = unpack_bf16x2(hb.x), h1 = unpack_bf16x2(hb.y);
+                v.x = h0.x * sigmoidf_fast(1.702f * h0.x);
+                v.y = h0.y * sigmoidf_fast(1.702f * h0.y);
+                v.z = h1.x * sigmoidf_fast(1.702f * h1.x);
+                v.w = h1.y * sigmoidf_fast(1.702f * h1.y);
+              }
+              if (flags & LV_EPI_DQUICKGELU) {
+                const uint2 hb = pre_aux[hh][i];
+                const float2 h0 = unpack_bf16x2(hb.x), h1 = unpack_bf16x2(hb.y);
+                const float s0 = sigmoidf_fast(1.702f * h0.x), s1 = sigmoidf_fast(1.702f * h0.y);
+                const float s2 = sigmoidf_fast(1.702f * h1.x), s3 = sigmoidf_fast(1.702f * h1.y);
+                v.x *= s0 * (1.0f + 1.702f * h0.x * (1.0f - s0));
+                v.y *= s1 * (1.0f + 1.702f * h0.y * (1.0f - s1));
+                v.z *= s2 * (1.0f + 1.702f * h1.x * (1.0f - s2));
+                v.w *= s3 * (1.0f + 1.702f * h1.y * (1.0f - s3));
+              }
+              if (flags & LV_EPI_SCALE) { v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale; }
+              if (flags & LV_EPI_RESID) {
+                const float4 rr = pre_res[hh][i];
+                v.x += rr.x; v.y += rr.y; v.z += rr.z; v.w += rr.w;
+              }
+              if (flags & LV_EPI_ATOMIC) {
+                float* o = reinterpret_cast<float*>(g.out) + (long long)m * g.ldo + n;
+                red_add_f32(o, v.x); red_add_f32(o + 1, v.y); red_add_f32(o + 2, v.z); red_add_f32(o + 3, v.w);
+              } else if (flags & LV_EPI_OUT_F32) {
+                *reinterpret_cast<float4*>(reinterpret_cast<float*>(g.out) + (long long)m * g.ldo + n) = v;
+              } else {
+                *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(g.out) + (long long)m * g.ldo + n) =
+                    make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+              }
+              if (flags & LV_EPI_COPY_BF16) {
+                *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(g.out2) + (long long)m * g.ldo2 + n) =
+                    make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+              }
             }
           }
+          __syncwarp();
         }
-        __syncwarp();
       }
       tc_fence_before();
       __syncwarp();
@@ -265,18 +312,44 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
 }
 
-template <int A_MN, int B_MN>
+template <int A_MN, int B_MN, int CT_FLAGS>
 static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const Args& g, cudaStream_t stream) {
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, []() {
-    attr_err = cudaFuncSetAttribute(gemm_bf16_kernel<A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    attr_err = cudaFuncSetAttribute(gemm_bf16_kernel<A_MN, B_MN, CT_FLAGS>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
   });
   if (attr_err != cudaSuccess) return set_error((int)attr_err, "gemm: cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err));
   const int total = g.num_m_blks * g.num_n_blks * g.k_splits;
   const int grid = total < sm_count() ? total : sm_count();
-  gemm_bf16_kernel<A_MN, B_MN><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmA, tmB, g);
+  gemm_bf16_kernel<A_MN, B_MN, CT_FLAGS><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmA, tmB, g);
   return check_launch("lv_gemm_bf16");
+}
+
+template <int A_MN, int B_MN, int F>
+static int try_spec(bool& hit, const CUtensorMap& tmA, const CUtensorMap& tmB, const Args& g, cudaStream_t st) {
+  if constexpr (is_specialised(A_MN, B_MN, F)) {
+    if (!hit && g.flags == F) { hit = true; return launch<A_MN, B_MN, F>(tmA, tmB, g, st); }
+  }
+  return 0;
+}
+
+template <int A_MN, int B_MN>
+static int dispatch(const CUtensorMap& tmA, const CUtensorMap& tmB, const Args& g, cudaStream_t st) {
+  bool hit = false;
+  int rc = 0;
+#define LV_TRY(F) if (!hit) rc = try_spec<A_MN, B_MN, (F)>(hit, tmA, tmB, g, st);
+  LV_TRY(0)
+  LV_TRY(LV_EPI_BIAS)
+  LV_TRY(LV_EPI_BIAS | LV_EPI_QUICKGELU)
+  LV_TRY(LV_EPI_OUT_F32)
+  LV_TRY(LV_EPI_BIAS | LV_EPI_RESID | LV_EPI_OUT_F32)
+  LV_TRY(LV_EPI_BIAS | LV_EPI_SCALE | LV_EPI_SCALE_TANH | LV_EPI_RESID | LV_EPI_OUT_F32)
+  LV_TRY(LV_EPI_DQUICKGELU)
+  LV_TRY(LV_EPI_ATOMIC | LV_EPI_OUT_F32)
+#undef LV_TRY
+  if (hit) return rc;
+  return launch<A_MN, B_MN, -1>(tmA, tmB, g, st);
 }
 
 }  // namespace gemm
@@ -288,13 +361,13 @@ extern "C" int lv_gemm_bf16(const void* A, int64_t lda, int a_mn, const void* B,
   using namespace lv::gemm;
   LV_REQUIRE(A && B && epi && epi->out, "lv_gemm_bf16: null pointer");
   LV_REQUIRE(M > 0 && N > 0 && K > 0 && M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), "lv_gemm_bf16: bad shape M=%lld N=%lld K=%lld", (long long)M, (long long)N, (long long)K);
-  LV_REQUIRE((N & 1) == 0 && (epi->ldo & 1) == 0, "lv_gemm_bf16: N and ldo must be even");
+  LV_REQUIRE((N & 3) == 0 && (epi->ldo & 3) == 0, "lv_gemm_bf16: N and ldo must be multiples of 4");
   const int flags = epi->flags;
   LV_REQUIRE(!(flags & LV_EPI_BIAS) || epi->bias, "lv_gemm_bf16: LV_EPI_BIAS without bias");
-  LV_REQUIRE(!(flags & LV_EPI_RESID) || (epi->resid && (epi->ldr & 1) == 0), "lv_gemm_bf16: LV_EPI_RESID without resid / odd ldr");
-  LV_REQUIRE(!(flags & (LV_EPI_QUICKGELU | LV_EPI_COPY_BF16)) || (epi->out2 && (epi->ldo2 & 1) == 0), "lv_gemm_bf16: out2 required");
+  LV_REQUIRE(!(flags & LV_EPI_RESID) || (epi->resid && (epi->ldr & 3) == 0), "lv_gemm_bf16: LV_EPI_RESID without resid / odd ldr");
+  LV_REQUIRE(!(flags & (LV_EPI_QUICKGELU | LV_EPI_COPY_BF16)) || (epi->out2 && (epi->ldo2 & 3) == 0), "lv_gemm_bf16: out2 required");
   LV_REQUIRE(!((flags & LV_EPI_QUICKGELU) && (flags & LV_EPI_COPY_BF16)), "lv_gemm_bf16: QUICKGELU and COPY_BF16 both use out2");
-  LV_REQUIRE(!(flags & LV_EPI_DQUICKGELU) || (epi->aux && (epi->ldaux & 1) == 0), "lv_gemm_bf16: aux required");
+  LV_REQUIRE(!(flags & LV_EPI_DQUICKGELU) || (epi->aux && (epi->ldaux & 3) == 0), "lv_gemm_bf16: aux required");
   LV_REQUIRE(!(flags & LV_EPI_SCALE) || epi->scale_ptr, "lv_gemm_bf16: scale_ptr required");
   if (k_splits < 1) k_splits = 1;
   LV_REQUIRE(k_splits == 1 || (flags & LV_EPI_ATOMIC), "lv_gemm_bf16: k_splits > 1 requires LV_EPI_ATOMIC");
@@ -325,8 +398,8 @@ extern "C" int lv_gemm_bf16(const void* A, int64_t lda, int a_mn, const void* B,
   g.scale_ptr = epi->scale_ptr;
 
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (!a_mn && !b_mn) return launch<0, 0>(tmA, tmB, g, st);
-  if (!a_mn && b_mn) return launch<0, 1>(tmA, tmB, g, st);
-  if (a_mn && b_mn) return launch<1, 1>(tmA, tmB, g, st);
-  return launch<1, 0>(tmA, tmB, g, st);
+  if (!a_mn && !b_mn) return dispatch<0, 0>(tmA, tmB, g, st);
+  if (!a_mn && b_mn) return dispatch<0, 1>(tmA, tmB, g, st);
+  if (a_mn && b_mn) return dispatch<1, 1>(tmA, tmB, g, st);
+  return dispatch<1, 0>(tmA, tmB, g, st);
 }

@@ -1,0 +1,81 @@
+"""The oracle (oracle/dual_encoder.py) against golden vectors produced by the unmodified reference
+(tests/golden/make_golden.py).  CPU only."""
+import os
+
+import pytest
+import torch
+
+from oracle import dual_encoder as O
+
+GOLD = torch.load(os.path.join(os.path.dirname(__file__), "golden", "dual_encoder_small.pt"), weights_only=False)
+TOL = dict(rtol=2e-4, atol=2e-5)
+
+
+def _setup(case):
+    c = GOLD[case]
+    cfg = c["cfg"]
+    p = O.init_params(cfg, seed=c["param_seed"], gated=c["gated"])
+    for k, v in c["param_checksum"].items():   # RNG drift guard: parameters are regenerated, not stored
+        assert abs(float(p[k].double().sum()) - v) <= 1e-6 * max(1.0, abs(v)), k
+    frames, text = O.synthetic_batch(cfg, c["batch"], seed=c["input_seed"])
+    assert abs(float(frames.double().sum()) - c["frames_checksum"]) < 1e-6 * frames.numel()
+    assert torch.equal(text, c["text"])          # token ids: bit exact
+    return c, cfg, p, frames, text
+
+
+@pytest.mark.parametrize("case", ["plain", "norm", "gated_norm"])
+def test_forward_matches_reference(case):
+    c, cfg, p, frames, text = _setup(case)
+    out = O.clip_forward(frames, text, p, cfg, norm_embed=c["norm_embed"])
+    torch.testing.assert_close(out["image_embed"], c["image_embed"], **TOL)
+    torch.testing.assert_close(out["text_embed"], c["text_embed"], **TOL)
+    torch.testing.assert_close(out["logit_scale"], c["logit_scale"], **TOL)
+    toks = O.timesformer_features(frames.permute(0, 2, 1, 3, 4), p, cfg, cls_at_last=False)
+    torch.testing.assert_close(toks[:, :5], c["visual_tokens"], **TOL)
+    ld = O.clip_loss(out["image_embed"], out["text_embed"], out["logit_scale"])
+    torch.testing.assert_close(ld["loss"], c["loss"], rtol=1e-4, atol=1e-4)
+    assert float(ld["clip_acc"]) == float(c["clip_acc"])   # argmax / labels: exact
+
+
+@pytest.mark.parametrize("case", ["norm", "gated_norm"])
+def test_gradients_match_reference(case):
+    c, cfg, p, frames, text = _setup(case)
+    p = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+    out = O.clip_forward(frames, text, p, cfg, norm_embed=c["norm_embed"])
+    O.clip_loss(out["image_embed"], out["text_embed"], out["logit_scale"])["loss"].backward()
+    assert set(c["grads"]) <= set(p), set(c["grads"]) - set(p)
+    for name, ref in c["grads"].items():
+        g = p[name].grad
+        assert g is not None, name
+        if "full" in ref:
+            torch.testing.assert_close(g, ref["full"].reshape(g.shape), rtol=2e-3, atol=2e-6, msg=lambda m: name + ": " + m)
+        else:
+            torch.testing.assert_close(g.flatten()[ref["idx"]], ref["sample"], rtol=2e-3, atol=2e-6, msg=lambda m: name + ": " + m)
+            torch.testing.assert_close(g.norm(), ref["norm"], rtol=1e-3, atol=1e-7)
+
+
+def test_multirank_loss_semantics():
+    """2-rank CLIPLoss(use_vissl) == single-process loss on the concatenated batch; local-embedding gradient
+    is W x the single-process one (GatherLayer all_reduce-SUM), `gather_features` path is 1 x."""
+    m = GOLD["multirank"]
+    W = m["world"]
+    imgs = [r["image"].clone().requires_grad_(True) for r in m["ranks"]]
+    txts = [r["text"].clone().requires_grad_(True) for r in m["ranks"]]
+    out = O.clip_loss_multi_rank(imgs, txts, torch.tensor(14.2857))
+    gi = torch.autograd.grad(out["loss"], imgs + txts)
+    for r in range(W):
+        ref = m["ranks"][r]
+        torch.testing.assert_close(out["loss"], ref["vissl"]["loss"], rtol=1e-5, atol=1e-6)
+        torch.testing.assert_close(out["loss"], ref["plain"]["loss"], rtol=1e-5, atol=1e-6)
+        assert float(out["clip_acc"]) == float(ref["vissl"]["acc"])
+        torch.testing.assert_close(W * gi[r], ref["vissl"]["grad_image"], rtol=1e-4, atol=1e-7)
+        torch.testing.assert_close(W * gi[W + r], ref["vissl"]["grad_text"], rtol=1e-4, atol=1e-7)
+        torch.testing.assert_close(gi[r], ref["plain"]["grad_image"], rtol=1e-4, atol=1e-7)
+
+
+def test_known_answers():
+    """SURVEY.md 8(c) self-checks: identical embeddings -> acc 100; labels are arange."""
+    e = torch.nn.functional.normalize(torch.randn(8, 16), dim=-1)
+    out = O.clip_loss(e, e, torch.tensor(100.0))
+    assert float(out["clip_acc"]) == 100.0
+    assert float(out["loss"]) < 0.05

@@ -121,25 +121,44 @@ def main():
         ok &= report("bias+tanh-scale+resid f32", out, ref)
         ok &= report("  bf16 copy", cp, ref)
     elif variant == "perf":
-        for (m, n, k, am, bm, ks, nm) in [(200768, 2304, 768, 0, 0, 1, "qkv fwd"), (200768, 768, 768, 0, 0, 1, "proj fwd"),
-                                          (200768, 3072, 768, 0, 0, 1, "fc1 fwd"), (200768, 768, 3072, 0, 0, 1, "fc2 fwd"),
-                                          (200768, 768, 2304, 0, 1, 1, "qkv dgrad"), (2304, 768, 200768, 1, 1, 8, "qkv wgrad"),
-                                          (3072, 768, 200768, 1, 1, 8, "fc1 wgrad"), (768, 3072, 200768, 1, 1, 8, "fc2 wgrad")]:
+        F = L
+        cases = [
+            (200768, 2304, 768, 0, 0, 1, F.EPI_BIAS, "qkv fwd +bias"),
+            (200768, 768, 768, 0, 0, 1, F.EPI_BIAS | F.EPI_RESID | F.EPI_OUT_F32, "proj fwd +bias+resid f32"),
+            (200768, 3072, 768, 0, 0, 1, F.EPI_BIAS | F.EPI_QUICKGELU, "fc1 fwd +bias+gelu(2 outs)"),
+            (200768, 768, 3072, 0, 0, 1, F.EPI_BIAS | F.EPI_RESID | F.EPI_OUT_F32, "fc2 fwd +bias+resid f32"),
+            (200768, 768, 2304, 0, 1, 1, 0, "qkv dgrad"),
+            (200768, 3072, 768, 0, 1, 1, F.EPI_DQUICKGELU, "fc2 dgrad *dgelu"),
+            (200768, 768, 3072, 0, 1, 1, 0, "fc1 dgrad"),
+            (2304, 768, 200768, 1, 1, 8, F.EPI_ATOMIC | F.EPI_OUT_F32, "qkv wgrad"),
+            (3072, 768, 200768, 1, 1, 8, F.EPI_ATOMIC | F.EPI_OUT_F32, "fc1 wgrad"),
+            (768, 3072, 200768, 1, 1, 8, F.EPI_ATOMIC | F.EPI_OUT_F32, "fc2 wgrad"),
+            (768, 768, 200768, 1, 1, 16, F.EPI_ATOMIC | F.EPI_OUT_F32, "proj wgrad"),
+        ]
+        for (m, n, k, am, bm, ks, fl, nm) in cases:
             A = (torch.randn((k, m) if am else (m, k), device=dev) * 0.1).bfloat16()
             B = (torch.randn((k, n) if bm else (n, k), device=dev) * 0.1).bfloat16()
-            out = torch.zeros(m, n, device=dev, dtype=torch.float32 if ks > 1 else torch.bfloat16)
-            fl = L.EPI_ATOMIC if ks > 1 else 0
+            f32 = bool(fl & F.EPI_OUT_F32)
+            out = torch.zeros(m, n, device=dev, dtype=torch.float32 if f32 else torch.bfloat16)
+            kw = {}
+            if fl & F.EPI_BIAS:
+                kw["bias"] = torch.randn(n, device=dev)
+            if fl & F.EPI_RESID:
+                kw["resid"] = torch.randn(m, n, device=dev)
+            if fl & F.EPI_QUICKGELU:
+                kw["out2"] = torch.empty(m, n, device=dev, dtype=torch.bfloat16)
+            if fl & F.EPI_DQUICKGELU:
+                kw["aux"] = torch.randn(m, n, device=dev).bfloat16()
             for _ in range(2):
-                gemm(A, am, B, bm, m, n, k, fl, out, k_splits=ks)
+                gemm(A, am, B, bm, m, n, k, fl, out, k_splits=ks, **kw)
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             for _ in range(5):
-                gemm(A, am, B, bm, m, n, k, fl, out, k_splits=ks)
+                gemm(A, am, B, bm, m, n, k, fl, out, k_splits=ks, **kw)
             e1.record()
             torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) / 5
-            # torch reference timing
             At = A.t() if am else A
             Bt = B if bm else B.t()
             for _ in range(2):
@@ -151,7 +170,7 @@ def main():
             e1.record()
             torch.cuda.synchronize()
             ms_t = e0.elapsed_time(e1) / 5
-            print("%-10s %7dx%5dx%7d  lv %.3f ms  %.1f TF/s | torch %.3f ms %.1f TF/s" % (
+            print("%-28s %7dx%5dx%7d  lv %.3f ms  %6.1f TF/s | torch(plain mm) %.3f ms %6.1f TF/s" % (
                 nm, m, n, k, ms, 2.0 * m * n * k / ms / 1e9, ms_t, 2.0 * m * n * k / ms_t / 1e9))
     print("RESULT", variant, "PASS" if ok else "FAIL")
 
