@@ -1,0 +1,70 @@
+"""Mirror of lavila/models/distributed_utils.py (GatherLayer / gather_from_all) on torch.distributed.
+
+The fused CLIPLoss (lavila_b200.models.loss) does not go through GatherLayer -- it gathers [image | text] with ONE
+collective and needs no backward collective at all -- but the symbols are kept so code importing them keeps working,
+with the reference's semantics (forward all_gather, backward all_reduce(SUM) of the stacked gradients, own slice).
+"""
+from typing import Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def convert_to_distributed_tensor(tensor: torch.Tensor) -> Tuple[torch.Tensor, str]:
+    """distributed_utils.py:17-30."""
+    orig_device = "cpu" if not tensor.is_cuda else "gpu"
+    if dist.is_available() and dist.get_backend() == dist.Backend.NCCL and not tensor.is_cuda:
+        tensor = tensor.cuda()
+    return tensor, orig_device
+
+
+def convert_to_normal_tensor(tensor: torch.Tensor, orig_device: str) -> torch.Tensor:
+    """distributed_utils.py:33-40."""
+    if tensor.is_cuda and orig_device == "cpu":
+        tensor = tensor.cpu()
+    return tensor
+
+
+def is_distributed_training_run() -> bool:
+    """distributed_utils.py:43-48."""
+    return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+
+
+class GatherLayer(torch.autograd.Function):
+    """distributed_utils.py:51-67."""
+
+    @staticmethod
+    def forward(ctx, x):
+        output = [torch.zeros_like(x) for _ in range(dist.get_world_size())]
+        dist.all_gather(output, x)
+        return tuple(output)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        all_gradients = torch.stack(grads)
+        dist.all_reduce(all_gradients)
+        return all_gradients[dist.get_rank()]
+
+
+def gather_from_all(tensor: torch.Tensor) -> torch.Tensor:
+    """distributed_utils.py:70-89."""
+    if tensor.ndim == 0:
+        tensor = tensor.unsqueeze(0)
+    if is_distributed_training_run():
+        tensor, orig_device = convert_to_distributed_tensor(tensor)
+        gathered = GatherLayer.apply(tensor)
+        gathered = [convert_to_normal_tensor(t, orig_device) for t in gathered]
+    else:
+        gathered = [tensor]
+    return torch.cat(gathered, 0)
+
+
+def gather_embeddings(image_features, text_features, world_size):
+    """ONE all_gather of the concatenated [B, 2E] block instead of the reference's two (loss.py:76-77 / :32-35).
+    Returns (all_image [W*B, E], all_text [W*B, E]) without autograd history."""
+    B, E = image_features.shape
+    local = torch.cat((image_features.detach(), text_features.detach()), dim=1).contiguous()
+    buf = [torch.empty_like(local) for _ in range(world_size)]
+    dist.all_gather(buf, local)
+    allb = torch.stack(buf, 0).view(world_size * B, 2 * E)
+    return allb[:, :E].contiguous(), allb[:, E:].contiguous()

@@ -1,0 +1,106 @@
+"""CLIPLoss -- mirror of lavila/models/loss.py:18-118 on the fused B200 kernels.
+
+forward(outputs) takes the dict returned by CLIP.forward and returns {'loss', 'clip_loss', 'clip_acc'} (0-dim tensors).
+Multi-GPU (world_size > 1): one all-gather of [image | text] embeddings over NCCL/NVLink, then every rank evaluates the
+global N x N loss redundantly (exactly what the reference does, loss.py:76-79) in one kernel.  Backward needs no
+collective: all ranks hold the same global loss, so the reference's all_reduce(SUM) of identical per-rank embedding
+gradients (distributed_utils.py:64-67) equals a multiplication by world_size, applied as `grad_scale`.
+"""
+import torch
+import torch.nn as nn
+
+from .. import ops
+from .distributed_utils import gather_embeddings
+
+F32 = torch.float32
+
+
+def gather_features(image_features, text_features, local_loss=False, gather_with_grad=False, rank=0, world_size=1):
+    """loss.py:18-43 (kept for API parity; returns tensors that carry gradient only through the local slot unless
+    gather_with_grad)."""
+    import torch.distributed as dist
+    import torch.distributed.nn
+    if gather_with_grad:
+        all_image = torch.cat(torch.distributed.nn.all_gather(image_features), dim=0)
+        all_text = torch.cat(torch.distributed.nn.all_gather(text_features), dim=0)
+    else:
+        gi = [torch.zeros_like(image_features) for _ in range(world_size)]
+        gt = [torch.zeros_like(text_features) for _ in range(world_size)]
+        dist.all_gather(gi, image_features)
+        dist.all_gather(gt, text_features)
+        if not local_loss:
+            gi[rank] = image_features
+            gt[rank] = text_features
+        all_image, all_text = torch.cat(gi, dim=0), torch.cat(gt, dim=0)
+    return all_image, all_text
+
+
+class _ClipLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, image, text, logit_scale, rank, world_size, grad_scale, state):
+        image = image.contiguous().float()
+        text = text.contiguous().float()
+        B, E = image.shape
+        dev = image.device
+        if world_size > 1:
+            all_i, all_t = gather_embeddings(image, text, world_size)
+        else:
+            all_i, all_t = image, text
+        Ng = all_i.shape[0]
+        scale = logit_scale.detach().reshape(1).contiguous().float()
+        lse_i = torch.empty(Ng, device=dev, dtype=F32)
+        lse_t = torch.empty(Ng, device=dev, dtype=F32)
+        partial = torch.empty(2 * Ng, device=dev, dtype=F32)
+        result = torch.empty(2, device=dev, dtype=F32)
+        if state.get("counter") is None or state["counter"].device != dev:
+            state["counter"] = torch.zeros(1, device=dev, dtype=torch.int32)
+        ops.clip_loss_fwd(all_i, all_t, scale, Ng, E, lse_i, lse_t, partial, state["counter"], result)
+        ctx.saved = (all_i, all_t, scale, lse_i, lse_t)
+        ctx.meta = (B, E, Ng, rank, world_size, grad_scale)
+        ctx.mark_non_differentiable(result[1])
+        return result[0], result[1]
+
+    @staticmethod
+    def backward(ctx, gloss, gacc):
+        all_i, all_t, scale, lse_i, lse_t = ctx.saved
+        ctx.saved = None
+        B, E, Ng, rank, world_size, grad_scale = ctx.meta
+        dev = all_i.device
+        d_i = torch.empty(Ng, E, device=dev, dtype=F32)
+        d_t = torch.empty(Ng, E, device=dev, dtype=F32)
+        d_s = torch.zeros(1, device=dev, dtype=F32)
+        g = gloss.reshape(1).contiguous().float()
+        # all rows: the logit_scale gradient is the full double sum on every rank (as in the reference); the
+        # embedding gradient of this rank is its own slice.
+        ops.clip_loss_bwd(all_i, all_t, scale, lse_i, lse_t, g, grad_scale, 1.0, Ng, E, 0, Ng, d_i, d_t, d_s)
+        sl = slice(rank * B, (rank + 1) * B)
+        return d_i[sl], d_t[sl], d_s.reshape(()), None, None, None, None
+
+
+class CLIPLoss(nn.Module):
+    """loss.py:46-118."""
+
+    def __init__(self, use_vissl=False, local_loss=False, gather_with_grad=False, cache_labels=False, rank=0,
+                 world_size=1):
+        super().__init__()
+        self.use_vissl = use_vissl
+        self.local_loss = local_loss
+        self.gather_with_grad = gather_with_grad
+        self.cache_labels = cache_labels
+        self.rank = rank
+        self.world_size = world_size
+        self.prev_num_logits = 0
+        self.labels = {}
+        self._state = {}
+        if local_loss:
+            raise NotImplementedError("local_loss=True is never enabled by the reference's get_loss (models.py:295-300)")
+
+    def forward(self, outputs):
+        image_features = outputs['image_embed']
+        text_features = outputs['text_embed']
+        logit_scale = outputs['logit_scale']
+        # embedding-gradient scale: GatherLayer / gather_with_grad sum W identical copies; gather_features keeps 1x
+        grad_scale = float(self.world_size) if (self.world_size > 1 and (self.use_vissl or self.gather_with_grad)) else 1.0
+        loss, acc = _ClipLossFn.apply(image_features, text_features, logit_scale, self.rank, self.world_size,
+                                      grad_scale, self._state)
+        return {'loss': loss, 'clip_loss': loss, 'clip_acc': acc}

@@ -1,0 +1,153 @@
+"""CLIP dual encoder + factories -- mirror of lavila/models/models.py:75-173, 293-313, 316-491 (hot-path subset).
+
+The factories build the same architectures as the reference's CLIP_OPENAI_TIMESFORMER_* functions.  The reference
+downloads OpenAI CLIP weights there (models.py:329); without network the model is randomly initialised with the
+reference's initialisers, or loaded from a LaViLa/ours checkpoint via `checkpoint=` (state_dict names are identical).
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .. import engine as E
+from . import loss as loss_mod
+from .openai_model import QuickGELU, Transformer
+from .timesformer import SpaceTimeTransformer
+
+
+class CLIP(nn.Module):
+    """models.py:75-173."""
+
+    def __init__(self, embed_dim: int, vision_width: int, vision_model: nn.Module, context_length: int,
+                 vocab_size: int, transformer_width: int, transformer_heads: int, transformer_layers: int,
+                 tempearture_init=0.07, **kwargs):
+        super().__init__()
+        self.context_length = context_length
+        self.vision_width = vision_width
+        self.visual = vision_model
+        self.transformer = Transformer(width=transformer_width, layers=transformer_layers, heads=transformer_heads,
+                                       attn_mask=self.build_attention_mask())
+        self.vocab_size = vocab_size
+        self.token_embedding = nn.Embedding(vocab_size, transformer_width)
+        self.positional_embedding = nn.Parameter(torch.empty(self.context_length, transformer_width))
+        self.ln_final = nn.LayerNorm(transformer_width)
+        self.image_projection = nn.Parameter(torch.empty(vision_width, embed_dim))
+        self.text_projection = nn.Parameter(torch.empty(transformer_width, embed_dim))
+        print("=> initialize initial temperature with {}".format(tempearture_init))
+        self.logit_scale = nn.Parameter(torch.ones([]) * np.log(1 / tempearture_init))
+        self.initialize_parameters()
+
+    def initialize_parameters(self):
+        """models.py:115-129."""
+        nn.init.normal_(self.token_embedding.weight, std=0.02)
+        nn.init.normal_(self.positional_embedding, std=0.01)
+        proj_std = (self.transformer.width ** -0.5) * ((2 * self.transformer.layers) ** -0.5)
+        attn_std = self.transformer.width ** -0.5
+        fc_std = (2 * self.transformer.width) ** -0.5
+        for block in self.transformer.resblocks:
+            nn.init.normal_(block.attn.in_proj_weight, std=attn_std)
+            nn.init.normal_(block.attn.out_proj.weight, std=proj_std)
+            nn.init.normal_(block.mlp.c_fc.weight, std=fc_std)
+            nn.init.normal_(block.mlp.c_proj.weight, std=proj_std)
+        nn.init.normal_(self.image_projection, std=self.vision_width ** -0.5)
+        nn.init.normal_(self.text_projection, std=self.transformer.width ** -0.5)
+
+    def build_attention_mask(self):
+        """models.py:131-137 (kept for API parity; the causal structure is built into the attention kernel)."""
+        mask = torch.empty(self.context_length, self.context_length)
+        mask.fill_(float("-inf"))
+        mask.triu_(1)
+        return mask
+
+    def encode_image(self, image, use_checkpoint=False, apply_project=True):
+        x = self.visual(image, use_checkpoint=use_checkpoint)
+        if isinstance(x, list):
+            assert len(x) == 1
+            x = x[0]
+        if not apply_project:
+            return x
+        return E.ProjectFn.apply(x, self.image_projection)
+
+    def encode_text(self, text, use_checkpoint=False):
+        x = E.TextEmbedFn.apply(text, self.token_embedding.weight, self.positional_embedding)   # [B, L, W]
+        x = self.transformer.forward_bld(x)
+        x = E.GatherEotFn.apply(x, text)                                                        # EOT rows [B, W]
+        x = E.LayerNormFn.apply(x, self.ln_final.weight, self.ln_final.bias, float(self.ln_final.eps))
+        return E.ProjectFn.apply(x, self.text_projection)
+
+    def forward(self, image, text, use_checkpoint=False, norm_embed=False):
+        image_embed = self.encode_image(image, use_checkpoint=use_checkpoint)
+        text_embed = self.encode_text(text, use_checkpoint=use_checkpoint)
+        if norm_embed:
+            image_embed = E.L2NormalizeFn.apply(image_embed)
+            text_embed = E.L2NormalizeFn.apply(text_embed)
+        return {'image_embed': image_embed, 'text_embed': text_embed, 'logit_scale': self.logit_scale.exp()}
+
+
+def get_loss(model, args, tokenizer=None):
+    """models.py:293-304 (CLIP branch)."""
+    if model.startswith('CLIP'):
+        return loss_mod.CLIPLoss(use_vissl=args.contrastive_use_vissl, cache_labels=True, rank=args.rank,
+                                 world_size=args.world_size)
+    raise NotImplementedError("only the CLIP* dual-encoder losses are on the B200 hot path")
+
+
+def get_metric_names(model):
+    """models.py:307-313."""
+    if model.startswith('CLIP'):
+        return ['loss', 'clip_loss', 'clip_acc']
+    raise NotImplementedError
+
+
+def _load_checkpoint(model, checkpoint):
+    if checkpoint is None:
+        print("=> no checkpoint given and no network: random initialisation (reference would load OpenAI CLIP weights)")
+        return
+    sd = torch.load(checkpoint, map_location='cpu') if isinstance(checkpoint, str) else checkpoint
+    sd = sd.get('state_dict', sd)
+    sd = {k[len('module.'):] if k.startswith('module.') else k: v for k, v in sd.items()}
+    print(model.load_state_dict(sd, strict=False))
+
+
+def _build(vision_kwargs, vision_width, text_width, text_heads, text_layers, num_frames, timesformer_gated_xattn,
+           drop_path_rate, timesformer_freeze_space, temperature_init, project_embed_dim, checkpoint, kwargs):
+    vision_model = SpaceTimeTransformer(num_frames=num_frames, time_init='zeros', attention_style='frozen-in-time',
+                                        ln_pre=True, act_layer=QuickGELU, is_tanh_gating=timesformer_gated_xattn,
+                                        drop_path_rate=drop_path_rate, **vision_kwargs)
+    vision_model.head = nn.Identity()
+    vision_model.pre_logits = nn.Identity()
+    vision_model.fc = nn.Identity()
+    model = CLIP(embed_dim=project_embed_dim, vision_width=vision_width, vision_model=vision_model, context_length=77,
+                 vocab_size=49408, transformer_width=text_width, transformer_heads=text_heads,
+                 transformer_layers=text_layers, tempearture_init=temperature_init, **kwargs)
+    _load_checkpoint(model, checkpoint)
+    if timesformer_freeze_space:
+        for n, p in vision_model.named_parameters():
+            p.requires_grad = ('temporal_embed' in n or 'timeattn' in n or 'norm3' in n or n == 'cls_token'
+                               or 'alpha_timeattn' in n)
+    return model
+
+
+def CLIP_OPENAI_TIMESFORMER_BASE(num_frames=4, timesformer_gated_xattn=False, drop_path_rate=0,
+                                 timesformer_freeze_space=False, temperature_init=0.07, project_embed_dim=256,
+                                 checkpoint=None, **kwargs):
+    """models.py:316-371: TSF-B/16 (768/12/12) + CLIP-B text tower (512/8/12)."""
+    return _build({}, 768, 512, 8, 12, num_frames, timesformer_gated_xattn, drop_path_rate, timesformer_freeze_space,
+                  temperature_init, project_embed_dim, checkpoint, kwargs)
+
+
+def CLIP_OPENAI_TIMESFORMER_LARGE(num_frames=4, timesformer_gated_xattn=False, drop_path_rate=0,
+                                  timesformer_freeze_space=False, temperature_init=0.07, project_embed_dim=256,
+                                  checkpoint=None, **kwargs):
+    """models.py:374-431: TSF-L/14 224px (1024/24/16) + CLIP-L text tower (768/12/12)."""
+    return _build(dict(img_size=224, patch_size=14, embed_dim=1024, depth=24, num_heads=16), 1024, 768, 12, 12,
+                  num_frames, timesformer_gated_xattn, drop_path_rate, timesformer_freeze_space, temperature_init,
+                  project_embed_dim, checkpoint, kwargs)
+
+
+def CLIP_OPENAI_TIMESFORMER_LARGE_336PX(num_frames=4, timesformer_gated_xattn=False, drop_path_rate=0,
+                                        timesformer_freeze_space=False, temperature_init=0.07, project_embed_dim=256,
+                                        checkpoint=None, **kwargs):
+    """models.py:434-491: TSF-L/14 336px."""
+    return _build(dict(img_size=336, patch_size=14, embed_dim=1024, depth=24, num_heads=16), 1024, 768, 12, 12,
+                  num_frames, timesformer_gated_xattn, drop_path_rate, timesformer_freeze_space, temperature_init,
+                  project_embed_dim, checkpoint, kwargs)

@@ -1,0 +1,182 @@
+"""Thin tensor-level wrappers over the C ABI (include/lavila_b200.h).  PyTorch supplies device memory and the
+stream; every FLOP/byte of the hot path is moved by liblavila_b200.so.  No fallbacks: a missing library or a
+failed launch raises LavilaB200Error."""
+import ctypes
+
+import torch
+
+from . import _lib as L
+
+BF16, F32 = torch.bfloat16, torch.float32
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _check_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise L.LavilaB200Error("lavila_b200 kernels need CUDA tensors (there is no CPU path)")
+
+
+def gemm(A, B, M, N, K, out, *, a_mn=0, b_mn=0, flags=0, out2=None, bias=None, resid=None, aux=None, scale=None,
+         k_splits=1, lda=None, ldb=None):
+    """out[M,N] = epilogue(A_op[M,K] @ B_op[N,K]^T); see lv_gemm_bf16 for the operand layouts."""
+    _check_cuda(A, B, out)
+    e = L.LvGemmEpilogue()
+    if out.dtype == F32:
+        flags |= L.EPI_OUT_F32
+    e.flags = flags
+    e.out, e.ldo = out.data_ptr(), out.stride(0)
+    if out2 is not None:
+        e.out2, e.ldo2 = out2.data_ptr(), out2.stride(0)
+    if bias is not None:
+        e.bias = bias.data_ptr()
+    if resid is not None:
+        e.resid, e.ldr = resid.data_ptr(), resid.stride(0)
+    if aux is not None:
+        e.aux, e.ldaux = aux.data_ptr(), aux.stride(0)
+    if scale is not None:
+        e.scale_ptr = scale.data_ptr()
+    rc = L.lib().lv_gemm_bf16(A.data_ptr(), lda if lda is not None else A.stride(0), a_mn, B.data_ptr(),
+                              ldb if ldb is not None else B.stride(0), b_mn, M, N, K, k_splits, ctypes.byref(e),
+                              _stream())
+    L.check(rc, "lv_gemm_bf16")
+    return out
+
+
+def wgrad_splits(m_out, n_in, k_tokens, sms=148):
+    tiles = ((m_out + 127) // 128) * ((n_in + 255) // 256)
+    kb = (k_tokens + 63) // 64
+    return max(1, min(kb, (4 * sms + tiles - 1) // tiles))
+
+
+def layernorm_fwd(x, gamma, beta, eps, rows, D, *, ldx=None, y_bf16=None, y_f32=None):
+    rc = L.lib().lv_layernorm_fwd(x.data_ptr(), ldx if ldx is not None else D, gamma.data_ptr(), beta.data_ptr(), eps,
+                                  _p(y_bf16), D, _p(y_f32), D, rows, D, _stream())
+    L.check(rc, "lv_layernorm_fwd")
+
+
+def layernorm_bwd(dy, x, gamma, eps, rows, D, *, ldx=None, lddy=None, add1=None, add2=None, dx=None, lddx=None,
+                  dx_bf16=None, dgamma=None, dbeta=None):
+    rc = L.lib().lv_layernorm_bwd(dy.data_ptr(), 1 if dy.dtype == BF16 else 0, lddy if lddy is not None else D,
+                                  x.data_ptr(), ldx if ldx is not None else D, gamma.data_ptr(), eps, _p(add1), D,
+                                  _p(add2), D, _p(dx), lddx if lddx is not None else D, _p(dx_bf16), D, _p(dgamma),
+                                  _p(dbeta), rows, D, _stream())
+    L.check(rc, "lv_layernorm_bwd")
+
+
+def group_attn_fwd(qkv, out, lse, mode, B, H, T=0, n=0, Lctx=0):
+    rc = L.lib().lv_group_attn_fwd(qkv.data_ptr(), qkv.stride(0), out.data_ptr(), out.stride(0), lse.data_ptr(), mode,
+                                   B, H, T, n, Lctx, _stream())
+    L.check(rc, "lv_group_attn_fwd")
+
+
+def group_attn_bwd(qkv, out, lse, dout, dqkv, dcls_kv, accumulate_kv, mode, B, H, T=0, n=0, Lctx=0):
+    rc = L.lib().lv_group_attn_bwd(qkv.data_ptr(), qkv.stride(0), out.data_ptr(), out.stride(0), lse.data_ptr(),
+                                   dout.data_ptr(), dout.stride(0), dqkv.data_ptr(), dqkv.stride(0), _p(dcls_kv),
+                                   accumulate_kv, mode, B, H, T, n, Lctx, _stream())
+    L.check(rc, "lv_group_attn_bwd")
+
+
+def cls_attn_fwd(qkv, out, lse, B, H, N):
+    rc = L.lib().lv_cls_attn_fwd(qkv.data_ptr(), qkv.stride(0), out.data_ptr(), out.stride(0), lse.data_ptr(), B, H, N,
+                                 _stream())
+    L.check(rc, "lv_cls_attn_fwd")
+
+
+def cls_attn_bwd(qkv, out, dout, lse, dqkv, dcls_kv, B, H, N):
+    rc = L.lib().lv_cls_attn_bwd(qkv.data_ptr(), qkv.stride(0), out.data_ptr(), out.stride(0), dout.data_ptr(),
+                                 dout.stride(0), lse.data_ptr(), dqkv.data_ptr(), dqkv.stride(0), dcls_kv.data_ptr(), B,
+                                 H, N, _stream())
+    L.check(rc, "lv_cls_attn_bwd")
+
+
+def cls_kv_finalize(dcls_kv, dqkv, B, H, N):
+    rc = L.lib().lv_cls_kv_finalize(dcls_kv.data_ptr(), dqkv.data_ptr(), dqkv.stride(0), B, H, N, _stream())
+    L.check(rc, "lv_cls_kv_finalize")
+
+
+def cast_bf16(x, out=None):
+    x = x.contiguous()
+    if out is None:
+        out = torch.empty(x.shape, device=x.device, dtype=BF16)
+    rc = L.lib().lv_cast_f32_bf16(x.data_ptr(), out.data_ptr(), x.numel(), _stream())
+    L.check(rc, "lv_cast_f32_bf16")
+    return out
+
+
+def colsum_bf16(x, M, N, out):
+    rc = L.lib().lv_colsum_bf16(x.data_ptr(), x.stride(0), M, N, out.data_ptr(), _stream())
+    L.check(rc, "lv_colsum_bf16")
+    return out
+
+
+def patch_im2col(frames, patches, B, C, T, H, W, P):
+    rc = L.lib().lv_patch_im2col(frames.data_ptr(), patches.data_ptr(), B, C, T, H, W, P, patches.stride(0), _stream())
+    L.check(rc, "lv_patch_im2col")
+
+
+def embed_assemble(patch, cls, pos, temporal, x0, B, T, n, D):
+    rc = L.lib().lv_embed_assemble(patch.data_ptr(), cls.data_ptr(), pos.data_ptr(), temporal.data_ptr(),
+                                   x0.data_ptr(), B, T, n, D, _stream())
+    L.check(rc, "lv_embed_assemble")
+
+
+def embed_assemble_bwd(dx0, dpos, dcls, dtemporal, dpatch, B, T, n, D):
+    rc = L.lib().lv_embed_assemble_bwd(dx0.data_ptr(), dpos.data_ptr(), dcls.data_ptr(), dtemporal.data_ptr(),
+                                       dpatch.data_ptr(), B, T, n, D, _stream())
+    L.check(rc, "lv_embed_assemble_bwd")
+
+
+def text_embed(text, tok, pos, x, rows, Lctx, W, vocab):
+    rc = L.lib().lv_text_embed(text.data_ptr(), tok.data_ptr(), pos.data_ptr(), x.data_ptr(), rows, Lctx, W, vocab,
+                               _stream())
+    L.check(rc, "lv_text_embed")
+
+
+def text_embed_bwd(text, dx, dtok, dpos, rows, Lctx, W, vocab):
+    rc = L.lib().lv_text_embed_bwd(text.data_ptr(), dx.data_ptr(), dtok.data_ptr(), dpos.data_ptr(), rows, Lctx, W,
+                                   vocab, _stream())
+    L.check(rc, "lv_text_embed_bwd")
+
+
+def argmax_i64(text, out, B, Lctx):
+    rc = L.lib().lv_argmax_i64(text.data_ptr(), out.data_ptr(), B, Lctx, _stream())
+    L.check(rc, "lv_argmax_i64")
+
+
+def gather_rows(src, idx, dst, R, rows_per, W, scatter=False):
+    rc = L.lib().lv_gather_rows_f32(src.data_ptr(), idx.data_ptr(), dst.data_ptr(), R, rows_per, W, int(scatter),
+                                    _stream())
+    L.check(rc, "lv_gather_rows_f32")
+
+
+def l2norm_fwd(x, y, norm, R, E):
+    rc = L.lib().lv_l2norm_fwd(x.data_ptr(), y.data_ptr(), norm.data_ptr(), R, E, _stream())
+    L.check(rc, "lv_l2norm_fwd")
+
+
+def l2norm_bwd(dy, y, norm, dx, R, E):
+    rc = L.lib().lv_l2norm_bwd(dy.data_ptr(), y.data_ptr(), norm.data_ptr(), dx.data_ptr(), R, E, _stream())
+    L.check(rc, "lv_l2norm_bwd")
+
+
+def clip_loss_fwd(img, txt, scale, Ng, E, lse_img, lse_txt, partial, counter, result):
+    rc = L.lib().lv_clip_loss_fwd(img.data_ptr(), txt.data_ptr(), scale.data_ptr(), Ng, E, lse_img.data_ptr(),
+                                  lse_txt.data_ptr(), partial.data_ptr(), counter.data_ptr(), result.data_ptr(),
+                                  _stream())
+    L.check(rc, "lv_clip_loss_fwd")
+
+
+def clip_loss_bwd(img, txt, scale, lse_img, lse_txt, gout, grad_scale, scale_grad_scale, Ng, E, r0, Nl, d_img, d_txt,
+                  d_scale):
+    rc = L.lib().lv_clip_loss_bwd(img.data_ptr(), txt.data_ptr(), scale.data_ptr(), lse_img.data_ptr(),
+                                  lse_txt.data_ptr(), gout.data_ptr(), float(grad_scale), float(scale_grad_scale), Ng, E,
+                                  r0, Nl, d_img.data_ptr(), d_txt.data_ptr(), _p(d_scale), _stream())
+    L.check(rc, "lv_clip_loss_bwd")

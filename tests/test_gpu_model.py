@@ -1,0 +1,104 @@
+"""GPU parity of the assembled modules against the oracle and the committed golden vectors of the reference."""
+import os
+
+import pytest
+import torch
+
+from oracle import dual_encoder as O
+from tests.util import assert_close_bf16, rel_l2, cosine
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+GOLD = torch.load(os.path.join(os.path.dirname(__file__), "golden", "dual_encoder_small.pt"), weights_only=False)
+
+
+def build_clip(cfg, params, gated=False):
+    from lavila_b200.models.models import CLIP
+    from lavila_b200.models.timesformer import SpaceTimeTransformer, QuickGELU
+    vis = SpaceTimeTransformer(img_size=cfg["img_size"], patch_size=cfg["patch_size"], embed_dim=cfg["embed_dim"],
+                               depth=cfg["depth"], num_heads=cfg["num_heads"], num_frames=cfg["num_frames"],
+                               time_init="zeros", ln_pre=True, act_layer=QuickGELU, is_tanh_gating=gated)
+    vis.head = torch.nn.Identity()
+    vis.pre_logits = torch.nn.Identity()
+    m = CLIP(embed_dim=cfg["project_dim"], vision_width=cfg["embed_dim"], vision_model=vis,
+             context_length=cfg["context_length"], vocab_size=cfg["vocab_size"], transformer_width=cfg["text_width"],
+             transformer_heads=cfg["text_heads"], transformer_layers=cfg["text_layers"])
+    res = m.load_state_dict(params, strict=False)
+    assert not res.unexpected_keys and not res.missing_keys, res
+    return m.to(DEV)
+
+
+@pytest.mark.parametrize("case", ["plain", "norm", "gated_norm"])
+def test_clip_matches_reference_golden(case):
+    from lavila_b200.models.loss import CLIPLoss
+    c = GOLD[case]
+    cfg = c["cfg"]
+    params = O.init_params(cfg, seed=c["param_seed"], gated=c["gated"])
+    model = build_clip(cfg, params, c["gated"])
+    frames, text = O.synthetic_batch(cfg, c["batch"], seed=c["input_seed"])
+    assert torch.equal(text, c["text"])
+    out = model(frames.to(DEV), text.to(DEV), norm_embed=c["norm_embed"])
+    assert_close_bf16(out["image_embed"], c["image_embed"], "image_embed")
+    assert_close_bf16(out["text_embed"], c["text_embed"], "text_embed")
+    assert abs(float(out["logit_scale"]) - float(c["logit_scale"])) < 1e-4
+    ld = CLIPLoss()(out)
+    if c["norm_embed"]:
+        assert abs(float(ld["loss"]) - float(c["loss"])) < 3e-2, (float(ld["loss"]), float(c["loss"]))
+    ld["loss"].backward()
+    named = dict(model.named_parameters())
+    worst = (0.0, None)
+    if c["norm_embed"]:
+        for name, ref in c["grads"].items():
+            g = named[name].grad
+            assert g is not None, name
+            if "full" in ref:
+                got, want = g.flatten(), ref["full"].flatten()
+            else:
+                got, want = g.flatten()[ref["idx"].to(DEV)], ref["sample"]
+            if float(want.norm()) < 1e-7:
+                continue
+            cs = cosine(got, want)
+            r = rel_l2(got, want)
+            if r > worst[0]:
+                worst = (r, name)
+            assert cs > 0.99 and r < 6e-2, "%s: rel_l2 %.3e cosine %.5f" % (name, r, cs)
+    print("worst grad rel_l2", worst)
+
+
+def test_block_midsize_vs_oracle():
+    """One SpaceTimeBlock at TSF-B geometry (D=768, 12 heads, 16 frames x 196 patches), B=2, fwd + all grads."""
+    from lavila_b200.models.timesformer import SpaceTimeBlock, QuickGELU
+    from functools import partial
+    torch.manual_seed(11)
+    D, H, T, n, B = 768, 12, 16, 196, 2
+    N = 1 + T * n
+    blk = SpaceTimeBlock(D, H, qkv_bias=True, act_layer=QuickGELU, norm_layer=partial(torch.nn.LayerNorm, eps=1e-6),
+                         time_init="rand", is_tanh_gating=True).to(DEV)
+    with torch.no_grad():
+        blk.alpha_timeattn.fill_(0.5)
+        for nm, p_ in blk.named_parameters():
+            if "norm" in nm and nm.endswith("weight"):
+                p_.add_(0.1 * torch.randn_like(p_))
+            elif nm.endswith("bias"):
+                p_.normal_(0, 0.02)
+    x = torch.randn(B, N, D, device=DEV, requires_grad=True)
+    y = blk(x, 'b (f n) d', '(b f) n d', 'b (f n) d', '(b n) f d', time_n=n, space_f=T)
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    p = {"b." + k: v.detach().cpu().clone().requires_grad_(True) for k, v in blk.named_parameters()}
+    xr = x.detach().cpu().clone().requires_grad_(True)
+    ref = O.space_time_block(xr, p, "b.", H, T, n)
+    ref.backward(dy.cpu())
+    assert_close_bf16(y, ref, "block out", rel=1e-2)
+    assert_close_bf16(x.grad, xr.grad, "block dx", rel=3e-2)
+    for k, v in blk.named_parameters():
+        assert_close_bf16(v.grad, p["b." + k].grad, "block d" + k, rel=4e-2, cos=0.998)
+
+
+def test_state_dict_roundtrip():
+    cfg = GOLD["plain"]["cfg"]
+    params = O.init_params(cfg, seed=0)
+    m = build_clip(cfg, params)
+    sd = m.state_dict()
+    for k, v in params.items():
+        assert torch.equal(sd[k].cpu(), v), k
