@@ -200,6 +200,12 @@ extern "C" int lv_layernorm_bwd(const void* dy, int dy_is_bf16, int64_t lddy, co
   const unsigned grid = (unsigned)(want < cap ? want : cap);
   const size_t smem = (size_t)ln::WARPS * 2 * D * sizeof(float);
   cudaStream_t st = (cudaStream_t)stream;
+  static bool configured = false;
+  if (!configured) {  // D = 1024 needs 64 KB of dynamic shared memory for the dgamma/dbeta reduction
+    cudaFuncSetAttribute(ln::ln_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    cudaFuncSetAttribute(ln::ln_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    configured = true;
+  }
   if (dy_is_bf16)
     ln::ln_bwd_kernel<true><<<grid, ln::WARPS * 32, smem, st>>>(dy, lddy, x, ldx, gamma, eps, add1, ld1, add2, ld2, dx, lddx,
                                                                 (__nv_bfloat16*)dx_bf16, lddxb, dgamma, dbeta, rows, D);
