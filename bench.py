@@ -305,9 +305,22 @@ def oracle_step_fn(frames):
     return step
 
 
+def host_threads():
+    """Threads the CPU arms may use: scheduler affinity, capped by the cgroup CPU quota and by 32 (the oracle's fp32
+    GEMMs stop scaling past that, and oversubscribing a shared host is catastrophic: 250 s/clip was observed)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            n = min(n, max(1, int(float(q) / float(per))))
+    except Exception:
+        pass
+    return max(1, min(n, 32))
+
+
 def cpu_baseline(frames, budget_s=25.0):
     import torch
-    cores = os.cpu_count() or 1
+    cores = host_threads()
     torch.set_num_threads(cores)
     step = oracle_step_fn(frames)
     t0 = time.time()
@@ -329,7 +342,7 @@ def run_reference(args):
     if rank != 0:
         return
     import torch
-    cores = os.cpu_count() or 1
+    cores = host_threads()
     torch.set_num_threads(cores)
     step = oracle_step_fn(args.frames)
     t0 = time.time()
