@@ -484,85 +484,70 @@ group_attn_bwd_kernel(const Params p, const int k_rows) {
 }
 
 // ================================================================================================ CLS query attention
-// One CTA per (clip, head): scores over all N keys in shared memory, two-pass softmax, then PV.
+// One CTA per (clip, head).  8 lanes share a key row (one 16-byte unit = 8 dims each) so every global access is a
+// coalesced 128-byte row; a warp walks 4 keys per step, the CTA 32.  Single pass over K and V:
+//   forward : online softmax per 8-lane group, partial (m, l, acc) merged through shared memory;
+//   backward: p_j from the saved lse, ds_j = p_j (dO.v_j - delta); dk_j, dv_j written in the same pass; dq reduced.
 constexpr int CLS_THREADS = 256;
+constexpr int CLS_GROUPS = CLS_THREADS / 8;
 
-__device__ __forceinline__ float block_reduce(float v, float* sred, bool is_max) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const float u = __shfl_xor_sync(0xffffffffu, v, o);
-    v = is_max ? fmaxf(v, u) : v + u;
-  }
-  __syncthreads();
-  if (lane == 0) sred[warp] = v;
-  __syncthreads();
-  float r = sred[0];
-  for (int w = 1; w < CLS_THREADS / 32; ++w) r = is_max ? fmaxf(r, sred[w]) : r + sred[w];
-  return r;
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
 }
-
-__device__ __forceinline__ float dot64(const float* q_s, const __nv_bfloat16* row) {
-  float acc = 0.f;
-#pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    const uint4 u = __ldg(reinterpret_cast<const uint4*>(row + c * 8));
-    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float2 x = unpack_bf16x2(w[j]);
-      acc += q_s[c * 8 + 2 * j] * x.x + q_s[c * 8 + 2 * j + 1] * x.y;
-    }
-  }
-  return acc;
+__device__ __forceinline__ float oct_sum(float v) {  // sum over the 8 lanes that share a key row
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  v += __shfl_xor_sync(0xffffffffu, v, 2);
+  return v + __shfl_xor_sync(0xffffffffu, v, 4);
 }
 
 __global__ void __launch_bounds__(CLS_THREADS)
 cls_attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld, __nv_bfloat16* __restrict__ out, long long ldo,
                     float* __restrict__ lse, int H, int D, int N, float scale) {
-  extern __shared__ float sm[];
-  float* sc = sm;                 // [N] scores -> probabilities
-  float* q_s = sm + N;            // [64]
-  float* red = q_s + HD;          // [8][64] partial outputs
-  __shared__ float sred[CLS_THREADS / 32];
+  __shared__ float s_m[CLS_GROUPS], s_l[CLS_GROUPS], s_acc[CLS_GROUPS][HD];
   const int b = blockIdx.x / H, h = blockIdx.x - b * H;
   const long long row0 = (long long)b * N;
-  const int tid = threadIdx.x;
-  if (tid < HD) q_s[tid] = __bfloat162float(qkv[row0 * ld + h * HD + tid]);
-  __syncthreads();
-  float mx = -INFINITY;
-  for (int j = tid; j < N; j += CLS_THREADS) {
-    const float s = dot64(q_s, qkv + (row0 + j) * ld + D + h * HD) * scale;
-    sc[j] = s;
-    mx = fmaxf(mx, s);
+  const int tid = threadIdx.x, grp = tid >> 3, c = tid & 7;
+  float q[8];
+  unpack8(__ldg(reinterpret_cast<const uint4*>(qkv + row0 * ld + h * HD + c * 8)), q);
+  float m = -INFINITY, l = 0.f, acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  const int iters = (N + CLS_GROUPS - 1) / CLS_GROUPS;
+  for (int it = 0; it < iters; ++it) {
+    const int j = it * CLS_GROUPS + grp;
+    const bool ok = j < N;
+    const __nv_bfloat16* base = qkv + (row0 + (ok ? j : 0)) * ld + h * HD + c * 8;
+    float k[8], v[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(base + D)), k);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(base + 2 * D)), v);
+    float sp = 0.f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) sp += q[e] * k[e];
+    const float sc = oct_sum(sp) * scale;
+    if (ok) {
+      const float mn = fmaxf(m, sc);
+      const float corr = __expf(m - mn), pj = __expf(sc - mn);
+      l = l * corr + pj;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] = acc[e] * corr + pj * v[e];
+      m = mn;
+    }
   }
-  mx = block_reduce(mx, sred, true);
-  float sum = 0.f;
-  for (int j = tid; j < N; j += CLS_THREADS) {
-    const float e = __expf(sc[j] - mx);
-    sc[j] = e;
-    sum += e;
-  }
-  sum = block_reduce(sum, sred, false);
-  // PV: thread = (d pair dp 0..31, key subset ks 0..7)
-  const int dp = tid & 31, ks = tid >> 5;
-  float a0 = 0.f, a1 = 0.f;
-  for (int j = ks; j < N; j += 8) {
-    const float2 v = unpack_bf16x2(__ldg(reinterpret_cast<const uint32_t*>(qkv + (row0 + j) * ld + 2 * D + h * HD + 2 * dp)));
-    const float pj = sc[j];
-    a0 += pj * v.x;
-    a1 += pj * v.y;
-  }
-  red[ks * HD + 2 * dp] = a0;
-  red[ks * HD + 2 * dp + 1] = a1;
+  if (c == 0) { s_m[grp] = m; s_l[grp] = l; }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) s_acc[grp][c * 8 + e] = acc[e];
   __syncthreads();
   if (tid < HD) {
-    float o = 0.f;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) o += red[k * HD + tid];
-    out[row0 * ldo + h * HD + tid] = __float2bfloat16_rn(o / sum);
+    float M = -INFINITY;
+    for (int g2 = 0; g2 < CLS_GROUPS; ++g2) M = fmaxf(M, s_m[g2]);
+    float Lsum = 0.f, o = 0.f;
+    for (int g2 = 0; g2 < CLS_GROUPS; ++g2) {
+      const float w = __expf(s_m[g2] - M);
+      Lsum += s_l[g2] * w;
+      o += s_acc[g2][tid] * w;
+    }
+    out[row0 * ldo + h * HD + tid] = __float2bfloat16_rn(o / Lsum);
+    if (tid == 0) lse[row0 * H + h] = M + logf(Lsum);
   }
-  if (tid == 0) lse[row0 * H + h] = mx + logf(sum);
 }
 
 // Backward of the CLS query attention.  Writes: dqkv[cls row, q part]; dqkv[rows 1..N-1, k and v parts] (this query's
@@ -572,72 +557,63 @@ cls_attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld, const _
                     long long ldo, const __nv_bfloat16* __restrict__ dout, long long lddo,
                     const float* __restrict__ lse, __nv_bfloat16* __restrict__ dqkv, long long lddq,
                     float* __restrict__ dcls_kv, int H, int D, int N, float scale) {
-  extern __shared__ float sm[];
-  float* ds = sm;                  // [N] p_j then ds_j
-  float* q_s = sm + N;             // [64]
-  float* do_s = q_s + HD;          // [64]
-  float* red = do_s + HD;          // [8][64]
-  __shared__ float sred[CLS_THREADS / 32];
+  __shared__ float s_dq[CLS_GROUPS][HD];
   const int b = blockIdx.x / H, h = blockIdx.x - b * H;
   const long long row0 = (long long)b * N;
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, grp = tid >> 3, c = tid & 7;
+  float q[8], dO[8], o[8];
+  unpack8(__ldg(reinterpret_cast<const uint4*>(qkv + row0 * ld + h * HD + c * 8)), q);
+  unpack8(__ldg(reinterpret_cast<const uint4*>(dout + row0 * lddo + h * HD + c * 8)), dO);
+  unpack8(__ldg(reinterpret_cast<const uint4*>(out + row0 * ldo + h * HD + c * 8)), o);
   float dpart = 0.f;
-  if (tid < HD) {
-    q_s[tid] = __bfloat162float(qkv[row0 * ld + h * HD + tid]);
-    const float d = __bfloat162float(dout[row0 * lddo + h * HD + tid]);
-    do_s[tid] = d;
-    dpart = d * __bfloat162float(out[row0 * ldo + h * HD + tid]);
-  }
-  const float delta = block_reduce(dpart, sred, false);
-  const float l = lse[row0 * H + h];
-  // p_j, dp_j = dO . v_j, ds_j = p_j (dp_j - delta); dv_j = p_j dO; dk_j = scale ds_j q
-  for (int j = tid; j < N; j += CLS_THREADS) {
-    const float s = dot64(q_s, qkv + (row0 + j) * ld + D + h * HD) * scale;
-    const float pj = __expf(s - l);
-    const float dpj = dot64(do_s, qkv + (row0 + j) * ld + 2 * D + h * HD);
-    const float dsj = pj * (dpj - delta);
-    ds[j] = dsj;
-    const float kscale = dsj * scale;
-    if (j == 0) {
-      float* base = dcls_kv + ((long long)b * H + h) * 2 * HD;
-      for (int d = 0; d < HD; ++d) {
-        base[d] = kscale * q_s[d];
-        base[HD + d] = pj * do_s[d];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) dpart += dO[e] * o[e];
+  const float delta = oct_sum(dpart);
+  const float L = lse[row0 * H + h];
+  float dq[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  const int iters = (N + CLS_GROUPS - 1) / CLS_GROUPS;
+  for (int it = 0; it < iters; ++it) {
+    const int j = it * CLS_GROUPS + grp;
+    const bool ok = j < N;
+    const __nv_bfloat16* base = qkv + (row0 + (ok ? j : 0)) * ld + h * HD + c * 8;
+    float k[8], v[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(base + D)), k);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(base + 2 * D)), v);
+    float sp = 0.f, dpp = 0.f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { sp += q[e] * k[e]; dpp += dO[e] * v[e]; }
+    const float sc = oct_sum(sp) * scale;
+    const float dpj = oct_sum(dpp);
+    if (ok) {
+      const float pj = __expf(sc - L);
+      const float dsj = pj * (dpj - delta) * scale;   // d loss / d (q.k_j)
+      float dk[8], dv[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        dq[e] += dsj * k[e];
+        dk[e] = dsj * q[e];
+        dv[e] = pj * dO[e];
       }
-    } else {
-      __nv_bfloat16* dk = dqkv + (row0 + j) * lddq + D + h * HD;
-      __nv_bfloat16* dvp = dqkv + (row0 + j) * lddq + 2 * D + h * HD;
+      if (j == 0) {
+        float* kb = dcls_kv + ((long long)b * H + h) * 2 * HD + c * 8;
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        uint32_t kw[4], vw[4];
-#pragma unroll
-        for (int jj = 0; jj < 4; ++jj) {
-          kw[jj] = pack_bf16x2(kscale * q_s[c * 8 + 2 * jj], kscale * q_s[c * 8 + 2 * jj + 1]);
-          vw[jj] = pack_bf16x2(pj * do_s[c * 8 + 2 * jj], pj * do_s[c * 8 + 2 * jj + 1]);
-        }
-        *reinterpret_cast<uint4*>(dk + c * 8) = make_uint4(kw[0], kw[1], kw[2], kw[3]);
-        *reinterpret_cast<uint4*>(dvp + c * 8) = make_uint4(vw[0], vw[1], vw[2], vw[3]);
+        for (int e = 0; e < 8; ++e) { kb[e] = dk[e]; kb[HD + e] = dv[e]; }
+      } else {
+        __nv_bfloat16* dst = dqkv + (row0 + j) * lddq + h * HD + c * 8;
+        *reinterpret_cast<uint4*>(dst + D) = make_uint4(pack_bf16x2(dk[0], dk[1]), pack_bf16x2(dk[2], dk[3]),
+                                                         pack_bf16x2(dk[4], dk[5]), pack_bf16x2(dk[6], dk[7]));
+        *reinterpret_cast<uint4*>(dst + 2 * D) = make_uint4(pack_bf16x2(dv[0], dv[1]), pack_bf16x2(dv[2], dv[3]),
+                                                             pack_bf16x2(dv[4], dv[5]), pack_bf16x2(dv[6], dv[7]));
       }
     }
   }
-  __syncthreads();
-  // dq = scale * sum_j ds_j k_j
-  const int dp = tid & 31, ks = tid >> 5;
-  float a0 = 0.f, a1 = 0.f;
-  for (int j = ks; j < N; j += 8) {
-    const float2 kv = unpack_bf16x2(__ldg(reinterpret_cast<const uint32_t*>(qkv + (row0 + j) * ld + D + h * HD + 2 * dp)));
-    const float w = ds[j];
-    a0 += w * kv.x;
-    a1 += w * kv.y;
-  }
-  red[ks * HD + 2 * dp] = a0;
-  red[ks * HD + 2 * dp + 1] = a1;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) s_dq[grp][c * 8 + e] = dq[e];
   __syncthreads();
   if (tid < HD) {
-    float o = 0.f;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) o += red[k * HD + tid];
-    dqkv[row0 * lddq + h * HD + tid] = __float2bfloat16_rn(o * scale);
+    float t = 0.f;
+    for (int g2 = 0; g2 < CLS_GROUPS; ++g2) t += s_dq[g2][tid];
+    dqkv[row0 * lddq + h * HD + tid] = __float2bfloat16_rn(t);
   }
 }
 
@@ -760,14 +736,7 @@ extern "C" int lv_cls_attn_fwd(const void* qkv, int64_t ld_qkv, void* out, int64
                                void* stream) {
   LV_REQUIRE(qkv && out && lse && B > 0 && H > 0 && N > 0, "lv_cls_attn_fwd: bad arguments");
   LV_REQUIRE(ld_qkv % 8 == 0, "lv_cls_attn_fwd: ld_qkv must be a multiple of 8");
-  const size_t smem = (size_t)(N + attn::HD + 8 * attn::HD) * sizeof(float);
-  static bool configured = false;
-  if (!configured) {
-    cudaFuncSetAttribute(attn::cls_attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    configured = true;
-  }
-  LV_REQUIRE(smem <= 200 * 1024, "lv_cls_attn_fwd: N=%d too large", N);
-  attn::cls_attn_fwd_kernel<<<B * H, attn::CLS_THREADS, smem, (cudaStream_t)stream>>>(
+  attn::cls_attn_fwd_kernel<<<B * H, attn::CLS_THREADS, 0, (cudaStream_t)stream>>>(
       (const __nv_bfloat16*)qkv, ld_qkv, (__nv_bfloat16*)out, ld_out, lse, H, H * attn::HD, N, 0.125f);
   return check_launch("lv_cls_attn_fwd");
 }
@@ -777,14 +746,7 @@ extern "C" int lv_cls_attn_bwd(const void* qkv, int64_t ld_qkv, const void* out,
                                int N, void* stream) {
   LV_REQUIRE(qkv && out && dout && lse && dqkv && dcls_kv && B > 0 && H > 0 && N > 0, "lv_cls_attn_bwd: bad arguments");
   LV_REQUIRE(ld_qkv % 8 == 0 && ld_dqkv % 8 == 0, "lv_cls_attn_bwd: leading dimensions must be multiples of 8");
-  const size_t smem = (size_t)(N + 2 * attn::HD + 8 * attn::HD) * sizeof(float);
-  static bool configured = false;
-  if (!configured) {
-    cudaFuncSetAttribute(attn::cls_attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    configured = true;
-  }
-  LV_REQUIRE(smem <= 200 * 1024, "lv_cls_attn_bwd: N=%d too large", N);
-  attn::cls_attn_bwd_kernel<<<B * H, attn::CLS_THREADS, smem, (cudaStream_t)stream>>>(
+  attn::cls_attn_bwd_kernel<<<B * H, attn::CLS_THREADS, 0, (cudaStream_t)stream>>>(
       (const __nv_bfloat16*)qkv, ld_qkv, (const __nv_bfloat16*)out, ld_out, (const __nv_bfloat16*)dout, ld_dout, lse,
       (__nv_bfloat16*)dqkv, ld_dqkv, dcls_kv, H, H * attn::HD, N, 0.125f);
   return check_launch("lv_cls_attn_bwd");

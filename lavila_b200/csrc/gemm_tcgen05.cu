@@ -209,36 +209,57 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int n_blk = tile - m_blk * g.num_n_blks;
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
-      mbar_wait(&tfull_bar[as], aphase);
-      tc_fence_after();
       const int m_base = m_blk * BM + q * 32;
       const int n0 = n_blk * BN;
-#pragma unroll 1
-      for (int cc = 0; cc < BN / 64; ++cc) {
-        const int c = half * (BN / 64) + cc;
-        if (n0 + c * 32 >= g.N) break;
-        // prefetch the epilogue's global operands for the whole 32x32 chunk (memory-level parallelism)
-        float4 pre_res[2][4];
-        uint2 pre_aux[2][4];
+      constexpr int CPW = BN / 64;  // 32-column chunks per warp (4)
+      // ---- everything this warp needs from global memory is requested BEFORE waiting on the accumulator:
+      //      the whole tile's bias, and the first chunk's residual / aux operands (then one chunk ahead).
+      float4 bias_r[CPW][2];
+#pragma unroll
+      for (int cc = 0; cc < CPW; ++cc)
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          const int n = n0 + (half * CPW + cc) * 32 + hh * 16 + ch * 4;
+          bias_r[cc][hh] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if ((flags & LV_EPI_BIAS) && !(flags & LV_EPI_ROWBIAS) && n < g.N)
+            bias_r[cc][hh] = __ldg(reinterpret_cast<const float4*>(g.bias + n));
+        }
+      // residual / aux operands are fetched one 16-column half chunk ahead of their use
+      float4 nxt_res[4];
+      uint2 nxt_aux[4];
+      auto prefetch = [&](int u) {
         if (flags & (LV_EPI_RESID | LV_EPI_DQUICKGELU)) {
+          const int n = n0 + (half * CPW + (u >> 1)) * 32 + (u & 1) * 16 + ch * 4;
 #pragma unroll
-          for (int hh = 0; hh < 2; ++hh) {
-            const int n = n0 + c * 32 + hh * 16 + ch * 4;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int m = m_base + 8 * i + r8;
-              if (m < g.M && n < g.N) {
-                if (flags & LV_EPI_RESID) pre_res[hh][i] = __ldg(reinterpret_cast<const float4*>(g.resid + (long long)m * g.ldr + n));
-                if (flags & LV_EPI_DQUICKGELU) pre_aux[hh][i] = __ldg(reinterpret_cast<const uint2*>(g.aux + (long long)m * g.ldaux + n));
-              }
+          for (int i = 0; i < 4; ++i) {
+            const int m = m_base + 8 * i + r8;
+            if (m < g.M && n < g.N) {
+              if (flags & LV_EPI_RESID) nxt_res[i] = __ldg(reinterpret_cast<const float4*>(g.resid + (long long)m * g.ldr + n));
+              if (flags & LV_EPI_DQUICKGELU) nxt_aux[i] = __ldg(reinterpret_cast<const uint2*>(g.aux + (long long)m * g.ldaux + n));
             }
           }
         }
+      };
+      prefetch(0);
+      mbar_wait(&tfull_bar[as], aphase);
+      tc_fence_after();
+#pragma unroll
+      for (int cc = 0; cc < CPW; ++cc) {
+        const int c = half * CPW + cc;
+        const bool chunk_ok = n0 + c * 32 < g.N;   // warp-uniform
         uint32_t r[32];
-        tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + as * BN + c * 32, r);
-        tmem_ld_wait();
+        if (chunk_ok) {
+          tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + as * BN + c * 32, r);
+          tmem_ld_wait();
+        }
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
+          float4 pre_res[4];
+          uint2 pre_aux[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) { pre_res[i] = nxt_res[i]; pre_aux[i] = nxt_aux[i]; }
+          if (cc * 2 + hh + 1 < 2 * CPW) prefetch(cc * 2 + hh + 1);
+          if (!chunk_ok) continue;
 #pragma unroll
           for (int j = 0; j < 4; ++j)
             *reinterpret_cast<float4*>(buf + lane * EPI_PITCH + ((j ^ ((lane >> 1) & 3)) << 2)) =
@@ -247,8 +268,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           __syncwarp();
           const int n = n0 + c * 32 + hh * 16 + ch * 4;
           const bool n_ok = n < g.N;
-          float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-          if ((flags & LV_EPI_BIAS) && !(flags & LV_EPI_ROWBIAS) && n_ok) bv = __ldg(reinterpret_cast<const float4*>(g.bias + n));
+          float4 bv = bias_r[cc][hh];
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const int row_l = 8 * i + r8;
@@ -267,7 +287,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 v.w = h1.y * sigmoidf_fast(1.702f * h1.y);
               }
               if (flags & LV_EPI_DQUICKGELU) {
-                const uint2 hb = pre_aux[hh][i];
+                const uint2 hb = pre_aux[i];
                 const float2 h0 = unpack_bf16x2(hb.x), h1 = unpack_bf16x2(hb.y);
                 const float s0 = sigmoidf_fast(1.702f * h0.x), s1 = sigmoidf_fast(1.702f * h0.y);
                 const float s2 = sigmoidf_fast(1.702f * h1.x), s3 = sigmoidf_fast(1.702f * h1.y);
@@ -278,7 +298,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               }
               if (flags & LV_EPI_SCALE) { v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale; }
               if (flags & LV_EPI_RESID) {
-                const float4 rr = pre_res[hh][i];
+                const float4 rr = pre_res[i];
                 v.x += rr.x; v.y += rr.y; v.z += rr.z; v.w += rr.w;
               }
               if (flags & LV_EPI_ATOMIC) {

@@ -79,17 +79,28 @@ ln_bwd_kernel(const void* __restrict__ dy_, long long lddy, const float* __restr
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int nv = D >> 7;
-  float4 dg[MAX_V], db[MAX_V], gm[MAX_V];
+  float4 dg[MAX_V], db[MAX_V];
 #pragma unroll
   for (int i = 0; i < MAX_V; ++i) {
     dg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     db[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (i < nv) gm[i] = __ldg(reinterpret_cast<const float4*>(gamma + (i * 32 + lane) * 4));
   }
   for (long long row = (long long)blockIdx.x * WARPS + warp; row < rows; row += (long long)gridDim.x * WARPS) {
     const float* xr = x + row * ldx;
-    float4 xv[MAX_V], gv[MAX_V];
+    float4 xv[MAX_V], gv[MAX_V], av[MAX_V];
     float s = 0.f;
+    // all global loads of the row are issued up front (x, dy, residual-path gradients): one exposed latency per row
+#pragma unroll
+    for (int i = 0; i < MAX_V; ++i)
+      if (i < nv) {
+        const int col = (i * 32 + lane) * 4;
+        av[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (add1) av[i] = __ldg(reinterpret_cast<const float4*>(add1 + row * ld1 + col));
+        if (add2) {
+          const float4 a = __ldg(reinterpret_cast<const float4*>(add2 + row * ld2 + col));
+          av[i].x += a.x; av[i].y += a.y; av[i].z += a.z; av[i].w += a.w;
+        }
+      }
 #pragma unroll
     for (int i = 0; i < MAX_V; ++i)
       if (i < nv) {
@@ -120,7 +131,8 @@ ln_bwd_kernel(const void* __restrict__ dy_, long long lddy, const float* __restr
         xv[i].x *= rstd; xv[i].y *= rstd; xv[i].z *= rstd; xv[i].w *= rstd;  // xhat
         dg[i].x += gv[i].x * xv[i].x; dg[i].y += gv[i].y * xv[i].y; dg[i].z += gv[i].z * xv[i].z; dg[i].w += gv[i].w * xv[i].w;
         db[i].x += gv[i].x; db[i].y += gv[i].y; db[i].z += gv[i].z; db[i].w += gv[i].w;
-        gv[i].x *= gm[i].x; gv[i].y *= gm[i].y; gv[i].z *= gm[i].z; gv[i].w *= gm[i].w;  // dy * gamma
+        const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma + (i * 32 + lane) * 4));  // L1-resident
+        gv[i].x *= gm.x; gv[i].y *= gm.y; gv[i].z *= gm.z; gv[i].w *= gm.w;  // dy * gamma
         c1 += gv[i].x + gv[i].y + gv[i].z + gv[i].w;
         c2 += gv[i].x * xv[i].x + gv[i].y * xv[i].y + gv[i].z * xv[i].z + gv[i].w * xv[i].w;
       }
@@ -135,14 +147,7 @@ ln_bwd_kernel(const void* __restrict__ dy_, long long lddy, const float* __restr
         o.y = rstd * (gv[i].y - c1 - xv[i].y * c2);
         o.z = rstd * (gv[i].z - c1 - xv[i].z * c2);
         o.w = rstd * (gv[i].w - c1 - xv[i].w * c2);
-        if (add1) {
-          const float4 a = __ldg(reinterpret_cast<const float4*>(add1 + row * ld1 + col));
-          o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
-        }
-        if (add2) {
-          const float4 a = __ldg(reinterpret_cast<const float4*>(add2 + row * ld2 + col));
-          o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
-        }
+        o.x += av[i].x; o.y += av[i].y; o.z += av[i].z; o.w += av[i].w;
         if (dx) *reinterpret_cast<float4*>(dx + row * lddx + col) = o;
         if (dx_bf16)
           *reinterpret_cast<uint2*>(dx_bf16 + row * lddxb + col) = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
