@@ -107,6 +107,15 @@ int lv_group_attn_fwd(const void* qkv, int64_t ld_qkv, void* out, int64_t ld_out
 int lv_group_attn_bwd(const void* qkv, int64_t ld_qkv, const void* out, int64_t ld_out, const float* lse,
                       const void* dout, int64_t ld_dout, void* dqkv, int64_t ld_dqkv, float* dcls_kv, int accumulate_kv,
                       int mode, int B, int H, int T, int n, int L, void* stream);
+/* Space attention forward on tcgen05 tensor cores (S, O accumulators in TMEM; TMA-loaded Q/K/V tiles; P staged in
+ * swizzled shared memory).  Same contract as lv_group_attn_fwd(mode 0); requires 129 <= n <= 207 (TSF-B: 196). */
+int lv_space_attn_fwd_tc(const void* qkv, int64_t ld_qkv, void* out, int64_t ld_out, float* lse, int B, int H, int T,
+                         int n, void* stream);
+/* Space attention backward on tcgen05 (S^T/dP^T, dV, dK, dQ accumulators in TMEM; P^T/dS^T staged in shared memory and
+ * consumed both K-major and MN-major).  Same contract and call order as lv_group_attn_bwd(mode 0). */
+int lv_space_attn_bwd_tc(const void* qkv, int64_t ld_qkv, const void* out, int64_t ld_out, const float* lse,
+                         const void* dout, int64_t ld_dout, void* dqkv, int64_t ld_dqkv, float* dcls_kv, int accumulate_kv,
+                         int B, int H, int T, int n, void* stream);
 int lv_cls_attn_fwd(const void* qkv, int64_t ld_qkv, void* out, int64_t ld_out, float* lse, int B, int H, int N,
                     void* stream);
 int lv_cls_attn_bwd(const void* qkv, int64_t ld_qkv, const void* out, int64_t ld_out, const void* dout, int64_t ld_dout,

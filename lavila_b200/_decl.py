@@ -8,6 +8,8 @@ SIGNATURES = {
     "lv_layernorm_bwd": [P, I, L, P, L, P, F, P, L, P, L, P, L, P, L, P, P, L, I, P],
     "lv_group_attn_fwd": [P, L, P, L, P, I, I, I, I, I, I, P],
     "lv_group_attn_bwd": [P, L, P, L, P, P, L, P, L, P, I, I, I, I, I, I, I, P],
+    "lv_space_attn_fwd_tc": [P, L, P, L, P, I, I, I, I, P],
+    "lv_space_attn_bwd_tc": [P, L, P, L, P, P, L, P, L, P, I, I, I, I, I, P],
     "lv_cls_attn_fwd": [P, L, P, L, P, I, I, I, P],
     "lv_cls_attn_bwd": [P, L, P, L, P, L, P, P, L, P, I, I, I, P],
     "lv_cls_kv_finalize": [P, P, L, I, I, I, P],

@@ -1,0 +1,678 @@
+// Space attention (one group = (clip, head, frame): n patch queries, n + CLS keys) on tcgen05 tensor cores.
+//
+//   forward :  S = Q K^T  (2 x [128 x 208] fp32 in TMEM)  ->  fp32 softmax by 8 warps (thread = row)
+//              ->  P (bf16) staged in shared memory in the canonical K-major 128B-swizzled layout
+//              ->  O = P V  ([128 x 64] fp32 in TMEM, V consumed MN-major straight from its TMA tile).
+// Persistent CTAs (one per SM) walk the groups; Q, K, V tiles arrive by TMA directly from the packed projection
+// output qkv[rows, 3D] (2D box = 64 columns x n rows); the CLS key/value row is appended by 16 threads.
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one lane), warps 2..9 = softmax/epilogue
+// (warps 2-5 own query tile 0, warps 6-9 own query tile 1; a warp may only touch TMEM lanes 32*(warp%4)..+31).
+//
+// Replaces the space half of VarAttention.forward (lavila/models/timesformer.py:121-134, attn() :35-39).
+// Numerics: bf16 operands, fp32 accumulation and softmax -- same contract as the mma.sync kernels in attention.cu,
+// which remain in use for the HBM-bound time attention (17 keys) and the small text tower.
+#include <mutex>
+
+#include "../../include/lavila_b200.h"
+#include "host_common.h"
+#include "ptx.cuh"
+
+namespace lv {
+namespace attn_tc {
+
+constexpr int HD = 64;
+constexpr int QROWS = 256;            // two M=128 query tiles (rows >= n are zero)
+constexpr int KROWS = 208;            // UMMA N for S: keys padded to a multiple of 16
+constexpr int SQ_BYTES = QROWS * 128;
+constexpr int SK_BYTES = KROWS * 128;
+constexpr int SP_BYTES = 4 * 128 * 128;  // P tile: 4 atoms of (128 rows x 64 keys)
+constexpr int NTHREADS = 320;
+constexpr int TM_S = 0, TM_O = 2 * KROWS;  // TMEM columns: S0 [0,208) S1 [208,416) O [416,480)
+constexpr int TMEM_COLS = 512;
+constexpr float LOG2E = 1.4426950408889634f;
+
+struct Params {
+  const __nv_bfloat16* qkv;
+  long long ld_qkv;
+  __nv_bfloat16* out;
+  long long ld_out;
+  float* lse;
+  int H, D, n, T;
+  long long clip_rows;
+  long long num_groups;
+  float scale;
+};
+
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+struct Coord {
+  int b, h, f;
+  long long base_row, cls_row;
+};
+template <class P>
+__device__ __forceinline__ Coord decode(const P& p, long long g) {
+  Coord c;
+  c.f = (int)(g % p.T);
+  const long long bh = g / p.T;
+  c.h = (int)(bh % p.H);
+  c.b = (int)(bh / p.H);
+  c.cls_row = (long long)c.b * p.clip_rows;
+  c.base_row = c.cls_row + 1 + (long long)c.f * p.n;
+  return c;
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+space_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + SQ_BYTES;
+  uint8_t* sV = sK + SK_BYTES;
+  uint8_t* sP = sV + SK_BYTES;  // two tiles
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * SP_BYTES);
+  uint64_t* bar_load = bars;
+  uint64_t* bar_s = bars + 1;
+  uint64_t* bar_p = bars + 2;      // [2]
+  uint64_t* bar_o = bars + 4;      // [2]
+  uint64_t* bar_ofree = bars + 6;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int Lq = p.n, Lk = p.n + 1;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tm_qkv);
+    mbar_init(bar_load, 1);
+    mbar_init(bar_s, 1);
+    for (int t = 0; t < 2; ++t) {
+      mbar_init(&bar_p[t], 4);
+      mbar_init(&bar_o[t], 1);
+      mbar_init(&bar_ofree[t], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, TMEM_COLS);
+    tmem_relinquish();
+  }
+  // zero the padding rows once: they are never written again (TMA boxes cover rows [0, n) only)
+  for (int idx = threadIdx.x; idx < (QROWS - Lq) * 8; idx += NTHREADS)
+    st_shared_v4(smem_u32(sQ) + Lq * 128 + idx * 16, 0, 0, 0, 0);
+  for (int idx = threadIdx.x; idx < (KROWS - Lq) * 8; idx += NTHREADS) {
+    st_shared_v4(smem_u32(sK) + Lq * 128 + idx * 16, 0, 0, 0, 0);
+    st_shared_v4(smem_u32(sV) + Lq * 128 + idx * 16, 0, 0, 0, 0);
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ producer
+    int it = 0;
+    for (long long g = blockIdx.x; g < p.num_groups; g += gridDim.x, ++it) {
+      if (it > 0) {
+        if (lane == 0) mbar_wait(&bar_o[1], (it - 1) & 1);  // previous group's last MMA has read Q, K, V
+        __syncwarp();
+      }
+      const Coord c = decode(p, g);
+      if (lane < 16) {  // CLS key / value row -> row Lq of the K / V tiles (generic proxy, swizzled by hand)
+        const int part = lane >> 3, ch = lane & 7;
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(p.qkv + c.cls_row * p.ld_qkv + (1 + part) * p.D + c.h * HD + ch * 8));
+        const uint32_t dst = smem_u32(part ? sV : sK) + Lq * 128 + ((ch ^ (Lq & 7)) << 4);
+        st_shared_v4(dst, v.x, v.y, v.z, v.w);
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive_expect_tx(bar_load, 3 * Lq * 128);
+        tma_load_2d(sQ, &tm_qkv, bar_load, c.h * HD, (int)c.base_row);
+        tma_load_2d(sK, &tm_qkv, bar_load, p.D + c.h * HD, (int)c.base_row);
+        tma_load_2d(sV, &tm_qkv, bar_load, 2 * p.D + c.h * HD, (int)c.base_row);
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = make_idesc_bf16(128, KROWS, 0, 0);
+      constexpr uint32_t idesc_o = make_idesc_bf16(128, HD, 0, 1);
+      const uint32_t q_base = smem_u32(sQ), k_base = smem_u32(sK), v_base = smem_u32(sV), p_base = smem_u32(sP);
+      int it = 0;
+      for (long long g = blockIdx.x; g < p.num_groups; g += gridDim.x, ++it) {
+        const uint32_t ph = it & 1;
+        mbar_wait(bar_load, ph);
+        tc_fence_after();
+#pragma unroll
+        for (int t = 0; t < 2; ++t)
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)
+            tc_mma_bf16(tmem_base + TM_S + t * KROWS, make_smem_desc_sw128(q_base + t * 16384 + ks * 32, 16, 1024),
+                        make_smem_desc_sw128(k_base + ks * 32, 16, 1024), idesc_s, ks > 0);
+        tc_commit(bar_s);
+#pragma unroll 1
+        for (int t = 0; t < 2; ++t) {
+          mbar_wait(&bar_p[t], ph);
+          // the single O accumulator must have been drained by the previous user
+          if (t == 0) { if (it > 0) mbar_wait(&bar_ofree[1], (it - 1) & 1); }
+          else mbar_wait(&bar_ofree[0], ph);
+          tc_fence_after();
+#pragma unroll
+          for (int s = 0; s < KROWS / 16; ++s)
+            tc_mma_bf16(tmem_base + TM_O, make_smem_desc_sw128(p_base + t * SP_BYTES + (s >> 2) * 16384 + (s & 3) * 32, 16, 1024),
+                        make_smem_desc_sw128(v_base + s * 2048, 8192, 1024), idesc_o, s > 0);
+          tc_commit(&bar_o[t]);
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ softmax + epilogue warps
+    const int e = warp - 2, t = e >> 2, q = warp & 3;
+    const int row = q * 32 + lane;          // row inside the 128-row tile == TMEM lane
+    const int qrow = t * 128 + row;
+    const uint32_t trow = tmem_base + (uint32_t(q * 32) << 16);
+    const uint32_t p_tile = smem_u32(sP) + t * SP_BYTES + row * 128;
+    const float sl2 = p.scale * LOG2E;
+    int it = 0;
+    for (long long g = blockIdx.x; g < p.num_groups; g += gridDim.x, ++it) {
+      const uint32_t ph = it & 1;
+      const Coord c = decode(p, g);
+      mbar_wait(bar_s, ph);
+      tc_fence_after();
+      const uint32_t ts = trow + TM_S + t * KROWS;
+      // ---- pass 1: row maximum
+      float m = -INFINITY;
+#pragma unroll 1
+      for (int cc = 0; cc < 6; ++cc) {
+        uint32_t r[32];
+        tmem_ld_32x32(ts + cc * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (cc * 32 + j < Lk) m = fmaxf(m, __uint_as_float(r[j]));
+      }
+      {
+        uint32_t r[16];
+        tmem_ld_32x16(ts + 192, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (192 + j < Lk) m = fmaxf(m, __uint_as_float(r[j]));
+      }
+      // ---- pass 2: p = exp2((s - m) * scale * log2e), row sum, bf16 P into the swizzled K-major tile
+      float sum = 0.f;
+      const float mb = m * sl2;
+#pragma unroll 1
+      for (int cc = 0; cc < 6; ++cc) {
+        uint32_t r[32];
+        tmem_ld_32x32(ts + cc * 32, r);
+        tmem_ld_wait();
+        float pv[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          pv[j] = (cc * 32 + j < Lk) ? exp2f(fmaf(__uint_as_float(r[j]), sl2, -mb)) : 0.f;
+          sum += pv[j];
+        }
+        const uint32_t atom = p_tile + (cc >> 1) * 16384;
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          const int chunk = (cc & 1) * 4 + jj;
+          st_shared_v4(atom + ((chunk ^ (row & 7)) << 4), pack_bf16x2(pv[jj * 8], pv[jj * 8 + 1]),
+                       pack_bf16x2(pv[jj * 8 + 2], pv[jj * 8 + 3]), pack_bf16x2(pv[jj * 8 + 4], pv[jj * 8 + 5]),
+                       pack_bf16x2(pv[jj * 8 + 6], pv[jj * 8 + 7]));
+        }
+      }
+      {
+        uint32_t r[16];
+        tmem_ld_32x16(ts + 192, r);
+        tmem_ld_wait();
+        float pv[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          pv[j] = (192 + j < Lk) ? exp2f(fmaf(__uint_as_float(r[j]), sl2, -mb)) : 0.f;
+          sum += pv[j];
+        }
+        const uint32_t atom = p_tile + 3 * 16384;
+#pragma unroll
+        for (int jj = 0; jj < 2; ++jj)
+          st_shared_v4(atom + ((jj ^ (row & 7)) << 4), pack_bf16x2(pv[jj * 8], pv[jj * 8 + 1]),
+                       pack_bf16x2(pv[jj * 8 + 2], pv[jj * 8 + 3]), pack_bf16x2(pv[jj * 8 + 4], pv[jj * 8 + 5]),
+                       pack_bf16x2(pv[jj * 8 + 6], pv[jj * 8 + 7]));
+      }
+      fence_proxy_async_smem();   // P must be visible to the tensor core (async proxy)
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_p[t]);
+      // ---- epilogue: O / sum -> bf16 -> global
+      mbar_wait(&bar_o[t], ph);
+      tc_fence_after();
+      uint32_t o0[32], o1[32];
+      tmem_ld_32x32(trow + TM_O, o0);
+      tmem_ld_32x32(trow + TM_O + 32, o1);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_ofree[t]);
+      if (qrow < Lq) {
+        const float inv = 1.f / sum;
+        const long long grow = c.base_row + qrow;
+        __nv_bfloat16* dst = p.out + grow * p.ld_out + c.h * HD;
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          *reinterpret_cast<uint4*>(dst + jj * 8) =
+              make_uint4(pack_bf16x2(__uint_as_float(o0[jj * 8]) * inv, __uint_as_float(o0[jj * 8 + 1]) * inv),
+                         pack_bf16x2(__uint_as_float(o0[jj * 8 + 2]) * inv, __uint_as_float(o0[jj * 8 + 3]) * inv),
+                         pack_bf16x2(__uint_as_float(o0[jj * 8 + 4]) * inv, __uint_as_float(o0[jj * 8 + 5]) * inv),
+                         pack_bf16x2(__uint_as_float(o0[jj * 8 + 6]) * inv, __uint_as_float(o0[jj * 8 + 7]) * inv));
+          *reinterpret_cast<uint4*>(dst + 32 + jj * 8) =
+              make_uint4(pack_bf16x2(__uint_as_float(o1[jj * 8]) * inv, __uint_as_float(o1[jj * 8 + 1]) * inv),
+                         pack_bf16x2(__uint_as_float(o1[jj * 8 + 2]) * inv, __uint_as_float(o1[jj * 8 + 3]) * inv),
+                         pack_bf16x2(__uint_as_float(o1[jj * 8 + 4]) * inv, __uint_as_float(o1[jj * 8 + 5]) * inv),
+                         pack_bf16x2(__uint_as_float(o1[jj * 8 + 6]) * inv, __uint_as_float(o1[jj * 8 + 7]) * inv));
+        }
+        p.lse[grow * p.H + c.h] = m * p.scale + logf(sum);
+      }
+    }
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+constexpr int FWD_SMEM = 1024 + SQ_BYTES + 2 * SK_BYTES + 2 * SP_BYTES + 128;
+static_assert(FWD_SMEM <= 227 * 1024, "space attention forward: shared memory budget");
+
+
+// ================================================================================================ backward
+// Per group, with key tiles kt (128 keys = TMEM lanes) and query tiles qt (N = 128 or 80 columns):
+//   (A)  S^T  = K_kt Q_qt^T ,  dP^T = V_kt dO_qt^T                        [128 x Nq] fp32 in TMEM
+//   (E)  P^T  = exp2(S^T*scale*log2e - lse_q) ,  dS^T = P^T (dP^T - delta_q) * scale      (thread = key row)
+//        written as bf16 to shared memory, K-major swizzled rows [key][q]
+//   (B)  dV_kt += P^T dO_qt ,  dK_kt += dS^T Q_qt        (A operand K-major from the staged tiles)
+//        dQ_qt += dS K_kt                                (A operand = the same dS^T tile read MN-major)
+// dV/dK are complete after the two query tiles of a key tile, dQ after both key tiles.
+// TMEM columns: S^T 128 | dP^T 128 | dV 64 | dK 64 | dQ0 64 | dQ1 64 = 512.
+constexpr int B_ROWS = 256;
+constexpr int B_TILE_BYTES = B_ROWS * 128;    // Q, K, V, dO tiles (rows beyond n / n+1 stay zero)
+constexpr int B_STAGE_BYTES = 2 * 128 * 128;  // P^T / dS^T: 128 key rows x 128 query columns (2 atoms of 64)
+constexpr int TB_ST = 0, TB_DPT = 128, TB_DV = 256, TB_DK = 320, TB_DQ = 384;
+constexpr int BWD_SMEM = 1024 + 4 * B_TILE_BYTES + 2 * B_STAGE_BYTES + 2 * B_ROWS * 4 + 128;
+static_assert(BWD_SMEM <= 227 * 1024, "space attention backward: shared memory budget");
+
+struct BwdParams {
+  const __nv_bfloat16* qkv;
+  long long ld_qkv;
+  const __nv_bfloat16* out;
+  long long ld_out;
+  const __nv_bfloat16* dout;
+  long long ld_dout;
+  const float* lse;
+  __nv_bfloat16* dqkv;
+  long long ld_dqkv;
+  float* dcls_kv;
+  int accumulate_kv;
+  int H, D, n, T;
+  long long clip_rows;
+  long long num_groups;
+  float scale;
+};
+
+__device__ __forceinline__ void tmem_ld_32x8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ void bar_sync_epi() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+__device__ __forceinline__ float dot8(const uint4& a, const uint4& b) {
+  const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+  float acc = 0.f;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 x = unpack_bf16x2(aw[j]), y = unpack_bf16x2(bw[j]);
+    acc += x.x * y.x + x.y * y.y;
+  }
+  return acc;
+}
+
+// Write a 64-wide fp32 accumulator row (two x32 TMEM loads) as bf16 to global, optionally adding what is there.
+__device__ __forceinline__ void store_row64(__nv_bfloat16* dst, const uint32_t (&a)[32], const uint32_t (&b)[32], bool accumulate) {
+#pragma unroll
+  for (int jj = 0; jj < 8; ++jj) {
+    const uint32_t* src = jj < 4 ? &a[jj * 8] : &b[(jj - 4) * 8];
+    float v[8];
+#pragma unroll
+    for (int e2 = 0; e2 < 8; ++e2) v[e2] = __uint_as_float(src[e2]);
+    if (accumulate) {
+      const uint4 old = *reinterpret_cast<const uint4*>(dst + jj * 8);
+      const float2 o0 = unpack_bf16x2(old.x), o1 = unpack_bf16x2(old.y), o2 = unpack_bf16x2(old.z), o3 = unpack_bf16x2(old.w);
+      v[0] += o0.x; v[1] += o0.y; v[2] += o1.x; v[3] += o1.y; v[4] += o2.x; v[5] += o2.y; v[6] += o3.x; v[7] += o3.y;
+    }
+    *reinterpret_cast<uint4*>(dst + jj * 8) =
+        make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+  }
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+space_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
+                         const BwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + B_TILE_BYTES;
+  uint8_t* sV = sK + B_TILE_BYTES;
+  uint8_t* sdO = sV + B_TILE_BYTES;
+  uint8_t* sPt = sdO + B_TILE_BYTES;
+  uint8_t* sdSt = sPt + B_STAGE_BYTES;
+  float* s_lse = reinterpret_cast<float*>(sdSt + B_STAGE_BYTES);
+  float* s_delta = s_lse + B_ROWS;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_delta + B_ROWS);
+  uint64_t* bar_load = bars;
+  uint64_t* bar_sdp = bars + 1;
+  uint64_t* bar_pds = bars + 2;
+  uint64_t* bar_mma3 = bars + 3;
+  uint64_t* bar_free = bars + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int Lq = p.n, Lk = p.n + 1;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tm_qkv);
+    prefetch_tmap(&tm_do);
+    mbar_init(bar_load, 1);
+    mbar_init(bar_sdp, 1);
+    mbar_init(bar_pds, 8);
+    mbar_init(bar_mma3, 1);
+    mbar_init(bar_free, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, TMEM_COLS);
+    tmem_relinquish();
+  }
+  // zero once: padding rows of the operand tiles and both staging tiles
+  for (int idx = threadIdx.x; idx < (B_ROWS - Lq) * 8; idx += NTHREADS) {
+    st_shared_v4(smem_u32(sQ) + Lq * 128 + idx * 16, 0, 0, 0, 0);
+    st_shared_v4(smem_u32(sdO) + Lq * 128 + idx * 16, 0, 0, 0, 0);
+    st_shared_v4(smem_u32(sK) + Lq * 128 + idx * 16, 0, 0, 0, 0);
+    st_shared_v4(smem_u32(sV) + Lq * 128 + idx * 16, 0, 0, 0, 0);
+  }
+  for (int idx = threadIdx.x; idx < 2 * B_STAGE_BYTES / 16; idx += NTHREADS) st_shared_v4(smem_u32(sPt) + idx * 16, 0, 0, 0, 0);
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ producer
+    int it = 0;
+    for (long long g = blockIdx.x; g < p.num_groups; g += gridDim.x, ++it) {
+      if (it > 0) {
+        if (lane == 0) mbar_wait(bar_free, (it - 1) & 1);  // every MMA of the previous group has read its operands
+        __syncwarp();
+      }
+      const Coord c = decode(p, g);
+      if (lane < 16) {
+        const int part = lane >> 3, ch = lane & 7;
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(p.qkv + c.cls_row * p.ld_qkv + (1 + part) * p.D + c.h * HD + ch * 8));
+        st_shared_v4(smem_u32(part ? sV : sK) + Lq * 128 + ((ch ^ (Lq & 7)) << 4), v.x, v.y, v.z, v.w);
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive_expect_tx(bar_load, 4 * Lq * 128);
+        tma_load_2d(sQ, &tm_qkv, bar_load, c.h * HD, (int)c.base_row);
+        tma_load_2d(sK, &tm_qkv, bar_load, p.D + c.h * HD, (int)c.base_row);
+        tma_load_2d(sV, &tm_qkv, bar_load, 2 * p.D + c.h * HD, (int)c.base_row);
+        tma_load_2d(sdO, &tm_do, bar_load, c.h * HD, (int)c.base_row);
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t q_base = smem_u32(sQ), k_base = smem_u32(sK), v_base = smem_u32(sV), do_base = smem_u32(sdO);
+      const uint32_t pt_base = smem_u32(sPt), ds_base = smem_u32(sdSt);
+      constexpr uint32_t idesc_a128 = make_idesc_bf16(128, 128, 0, 0);
+      constexpr uint32_t idesc_a80 = make_idesc_bf16(128, 80, 0, 0);
+      constexpr uint32_t idesc_kv = make_idesc_bf16(128, HD, 0, 1);   // A K-major (staged tile), B MN-major
+      constexpr uint32_t idesc_dq = make_idesc_bf16(128, HD, 1, 1);   // A MN-major (dS^T read transposed), B MN-major
+      int it = 0;
+      for (long long g = blockIdx.x; g < p.num_groups; g += gridDim.x, ++it) {
+        mbar_wait(bar_load, it & 1);
+        tc_fence_after();
+#pragma unroll 1
+        for (int step = 0; step < 4; ++step) {
+          const int kt = step >> 1, qt = step & 1;
+          const uint32_t idesc_a = qt ? idesc_a80 : idesc_a128;
+          // (A) S^T and dP^T
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            tc_mma_bf16(tmem_base + TB_ST, make_smem_desc_sw128(k_base + kt * 16384 + ks * 32, 16, 1024),
+                        make_smem_desc_sw128(q_base + qt * 16384 + ks * 32, 16, 1024), idesc_a, ks > 0);
+          }
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            tc_mma_bf16(tmem_base + TB_DPT, make_smem_desc_sw128(v_base + kt * 16384 + ks * 32, 16, 1024),
+                        make_smem_desc_sw128(do_base + qt * 16384 + ks * 32, 16, 1024), idesc_a, ks > 0);
+          }
+          tc_commit(bar_sdp);
+          // (B) needs the staged P^T / dS^T
+          mbar_wait(bar_pds, step & 1);
+          tc_fence_after();
+          const int nq_steps = qt ? 5 : 8;       // 80 or 128 query columns
+          for (int s2 = 0; s2 < nq_steps; ++s2) {
+            const uint32_t a_off = (s2 >> 2) * 16384 + (s2 & 3) * 32;
+            const uint32_t b_off = (qt * 128 + s2 * 16) * 128;
+            tc_mma_bf16(tmem_base + TB_DV, make_smem_desc_sw128(pt_base + a_off, 16, 1024),
+                        make_smem_desc_sw128(do_base + b_off, 8192, 1024), idesc_kv, (qt > 0 || s2 > 0));
+            tc_mma_bf16(tmem_base + TB_DK, make_smem_desc_sw128(ds_base + a_off, 16, 1024),
+                        make_smem_desc_sw128(q_base + b_off, 8192, 1024), idesc_kv, (qt > 0 || s2 > 0));
+          }
+          const int nk_steps = kt ? 5 : 8;       // keys 128..207 or 0..127
+          for (int s2 = 0; s2 < nk_steps; ++s2) {
+            tc_mma_bf16(tmem_base + TB_DQ + qt * 64, make_smem_desc_sw128(ds_base + s2 * 2048, 16384, 1024),
+                        make_smem_desc_sw128(k_base + (kt * 128 + s2 * 16) * 128, 8192, 1024), idesc_dq, (kt > 0 || s2 > 0));
+          }
+          tc_commit(bar_mma3);
+        }
+        tc_commit(bar_free);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ elementwise + epilogue warps
+    const int e = warp - 2, hf = e >> 2, q = warp & 3;
+    const int row = q * 32 + lane;   // TMEM lane = key row inside the key tile (or query row for the dQ epilogue)
+    const int et = e * 32 + lane;    // 0..255
+    const uint32_t trow = tmem_base + (uint32_t(q * 32) << 16);
+    const float sl2 = p.scale * LOG2E;
+    int it = 0;
+    for (long long g = blockIdx.x; g < p.num_groups; g += gridDim.x, ++it) {
+      const Coord c = decode(p, g);
+      // ---- per-query lse (in log2 units) and delta = sum_d dO*O
+      {
+        float l2 = 0.f, dl = 0.f;
+        if (et < Lq) {
+          const long long grow = c.base_row + et;
+          const __nv_bfloat16* orow = p.out + grow * p.ld_out + c.h * HD;
+          const __nv_bfloat16* drow = p.dout + grow * p.ld_dout + c.h * HD;
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            dl += dot8(__ldg(reinterpret_cast<const uint4*>(orow + j * 8)), __ldg(reinterpret_cast<const uint4*>(drow + j * 8)));
+          l2 = p.lse[grow * p.H + c.h] * LOG2E;
+        }
+        s_lse[et] = l2;
+        s_delta[et] = dl;
+      }
+      bar_sync_epi();
+#pragma unroll 1
+      for (int step = 0; step < 4; ++step) {
+        const int kt = step >> 1, qt = step & 1;
+        mbar_wait(bar_sdp, step & 1);
+        if (step > 0) mbar_wait(bar_mma3, (step - 1) & 1);   // previous (B) MMAs have consumed the staged tiles
+        tc_fence_after();
+        if (step == 2) {
+          // ---- epilogue of key tile 0: dV (hf 0) / dK (hf 1)
+          uint32_t a[32], b[32];
+          tmem_ld_32x32(trow + (hf ? TB_DK : TB_DV), a);
+          tmem_ld_32x32(trow + (hf ? TB_DK : TB_DV) + 32, b);
+          tmem_ld_wait();
+          const int key = row;   // < 128 <= Lq
+          store_row64(p.dqkv + (c.base_row + key) * p.ld_dqkv + (hf ? 1 : 2) * p.D + c.h * HD, a, b, p.accumulate_kv != 0);
+        }
+        const int key = kt * 128 + row;
+        const bool key_ok = key < Lk;
+        const int ncols = qt ? 40 : 64;         // this warp's share of the query columns
+        const int col_base = hf * ncols;
+        const uint32_t pt_row = smem_u32(sPt) + row * 128, ds_row = smem_u32(sdSt) + row * 128;
+        for (int cb = 0; cb < ncols; cb += 8) {
+          const int col0 = col_base + cb;       // query column inside the tile
+          uint32_t s8[8], d8[8];
+          tmem_ld_32x8(trow + TB_ST + col0, s8);
+          tmem_ld_32x8(trow + TB_DPT + col0, d8);
+          tmem_ld_wait();
+          const int qg = qt * 128 + col0;
+          const float4 la = *reinterpret_cast<const float4*>(s_lse + qg), lb = *reinterpret_cast<const float4*>(s_lse + qg + 4);
+          const float4 da = *reinterpret_cast<const float4*>(s_delta + qg), db = *reinterpret_cast<const float4*>(s_delta + qg + 4);
+          const float l8[8] = {la.x, la.y, la.z, la.w, lb.x, lb.y, lb.z, lb.w};
+          const float dl8[8] = {da.x, da.y, da.z, da.w, db.x, db.y, db.z, db.w};
+          float pv[8], dv[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const bool ok = key_ok && (qg + j < Lq);
+            const float pj = ok ? exp2f(fmaf(__uint_as_float(s8[j]), sl2, -l8[j])) : 0.f;
+            pv[j] = pj;
+            dv[j] = pj * (__uint_as_float(d8[j]) - dl8[j]) * p.scale;
+          }
+          const uint32_t off = (col0 >> 6) * 16384 + ((((col0 & 63) >> 3) ^ (row & 7)) << 4);
+          st_shared_v4(pt_row + off, pack_bf16x2(pv[0], pv[1]), pack_bf16x2(pv[2], pv[3]), pack_bf16x2(pv[4], pv[5]), pack_bf16x2(pv[6], pv[7]));
+          st_shared_v4(ds_row + off, pack_bf16x2(dv[0], dv[1]), pack_bf16x2(dv[2], dv[3]), pack_bf16x2(dv[4], dv[5]), pack_bf16x2(dv[6], dv[7]));
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_pds);
+      }
+      // ---- final epilogues: key tile 1 (dV / dK) and dQ0 / dQ1
+      mbar_wait(bar_mma3, 1);
+      tc_fence_after();
+      {
+        uint32_t a[32], b[32];
+        tmem_ld_32x32(trow + (hf ? TB_DK : TB_DV), a);
+        tmem_ld_32x32(trow + (hf ? TB_DK : TB_DV) + 32, b);
+        tmem_ld_wait();
+        const int key = 128 + row;
+        if (key < Lq) {
+          store_row64(p.dqkv + (c.base_row + key) * p.ld_dqkv + (hf ? 1 : 2) * p.D + c.h * HD, a, b, p.accumulate_kv != 0);
+        } else if (key == Lq && p.dcls_kv) {  // CLS key / value: fp32 atomics into the per-(clip, head) accumulator
+          float* base = p.dcls_kv + (((long long)c.b * p.H + c.h) * 2 + (hf ? 0 : 1)) * HD;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            atomicAdd(base + j, __uint_as_float(a[j]));
+            atomicAdd(base + 32 + j, __uint_as_float(b[j]));
+          }
+        }
+      }
+      {
+        uint32_t a[32], b[32];
+        tmem_ld_32x32(trow + TB_DQ + hf * 64, a);
+        tmem_ld_32x32(trow + TB_DQ + hf * 64 + 32, b);
+        tmem_ld_wait();
+        const int qrow = hf * 128 + row;
+        if (qrow < Lq) store_row64(p.dqkv + (c.base_row + qrow) * p.ld_dqkv + c.h * HD, a, b, false);
+      }
+      tc_fence_before();
+      bar_sync_epi();   // s_lse / s_delta of this group are dead; TMEM accumulators drained
+    }
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+}  // namespace attn_tc
+}  // namespace lv
+
+using namespace lv;
+
+// Space attention forward on tcgen05 (patch-token rows; the CLS row is produced by lv_cls_attn_fwd).
+// Requirements: 129 <= n <= 207 (TSF-B: 196), head_dim 64.  Other shapes use lv_group_attn_fwd.
+extern "C" int lv_space_attn_fwd_tc(const void* qkv, int64_t ld_qkv, void* out, int64_t ld_out, float* lse, int B, int H,
+                                    int T, int n, void* stream) {
+  LV_REQUIRE(qkv && out && lse && B > 0 && H > 0 && T > 0, "lv_space_attn_fwd_tc: bad arguments");
+  LV_REQUIRE(n > 128 && n + 1 <= attn_tc::KROWS, "lv_space_attn_fwd_tc: n=%d unsupported (129..207)", n);
+  LV_REQUIRE(ld_qkv % 8 == 0 && ld_out % 8 == 0, "lv_space_attn_fwd_tc: leading dimensions must be multiples of 8");
+  attn_tc::Params p{};
+  p.qkv = (const __nv_bfloat16*)qkv; p.ld_qkv = ld_qkv;
+  p.out = (__nv_bfloat16*)out; p.ld_out = ld_out;
+  p.lse = lse;
+  p.H = H; p.D = H * attn_tc::HD; p.n = n; p.T = T;
+  p.clip_rows = 1 + (long long)T * n;
+  p.num_groups = (long long)B * H * T;
+  p.scale = 0.125f;
+  const long long rows = (long long)B * p.clip_rows;
+  CUtensorMap tm;
+  int rc = make_tmap_2d_bf16(&tm, qkv, (uint64_t)(3 * p.D), (uint64_t)rows, (uint64_t)ld_qkv, 64, (uint32_t)n);
+  if (rc) return rc;
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, []() {
+    attr_err = cudaFuncSetAttribute(attn_tc::space_attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, attn_tc::FWD_SMEM);
+  });
+  if (attr_err != cudaSuccess) return set_error((int)attr_err, "lv_space_attn_fwd_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err));
+  const long long grid = p.num_groups < sm_count() ? p.num_groups : sm_count();
+  attn_tc::space_attn_fwd_tc_kernel<<<(unsigned)grid, attn_tc::NTHREADS, attn_tc::FWD_SMEM, (cudaStream_t)stream>>>(tm, p);
+  return check_launch("lv_space_attn_fwd_tc");
+}
+
+// Space attention backward on tcgen05.  Same contract / call order as lv_group_attn_bwd(mode 0):
+// lv_cls_attn_bwd -> lv_space_attn_bwd_tc(accumulate_kv = 1) -> lv_cls_kv_finalize.
+extern "C" int lv_space_attn_bwd_tc(const void* qkv, int64_t ld_qkv, const void* out, int64_t ld_out, const float* lse,
+                                    const void* dout, int64_t ld_dout, void* dqkv, int64_t ld_dqkv, float* dcls_kv,
+                                    int accumulate_kv, int B, int H, int T, int n, void* stream) {
+  LV_REQUIRE(qkv && out && lse && dout && dqkv && dcls_kv && B > 0 && H > 0 && T > 0, "lv_space_attn_bwd_tc: bad arguments");
+  LV_REQUIRE(n > 128 && n + 1 <= attn_tc::KROWS, "lv_space_attn_bwd_tc: n=%d unsupported (129..207)", n);
+  LV_REQUIRE(ld_qkv % 8 == 0 && ld_out % 8 == 0 && ld_dout % 8 == 0 && ld_dqkv % 8 == 0, "lv_space_attn_bwd_tc: leading dimensions must be multiples of 8");
+  attn_tc::BwdParams p{};
+  p.qkv = (const __nv_bfloat16*)qkv; p.ld_qkv = ld_qkv;
+  p.out = (const __nv_bfloat16*)out; p.ld_out = ld_out;
+  p.dout = (const __nv_bfloat16*)dout; p.ld_dout = ld_dout;
+  p.lse = lse;
+  p.dqkv = (__nv_bfloat16*)dqkv; p.ld_dqkv = ld_dqkv;
+  p.dcls_kv = dcls_kv; p.accumulate_kv = accumulate_kv;
+  p.H = H; p.D = H * attn_tc::HD; p.n = n; p.T = T;
+  p.clip_rows = 1 + (long long)T * n;
+  p.num_groups = (long long)B * H * T;
+  p.scale = 0.125f;
+  const long long rows = (long long)B * p.clip_rows;
+  CUtensorMap tm_qkv, tm_do;
+  int rc = make_tmap_2d_bf16(&tm_qkv, qkv, (uint64_t)(3 * p.D), (uint64_t)rows, (uint64_t)ld_qkv, 64, (uint32_t)n);
+  if (rc) return rc;
+  rc = make_tmap_2d_bf16(&tm_do, dout, (uint64_t)p.D, (uint64_t)rows, (uint64_t)ld_dout, 64, (uint32_t)n);
+  if (rc) return rc;
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, []() {
+    attr_err = cudaFuncSetAttribute(attn_tc::space_attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, attn_tc::BWD_SMEM);
+  });
+  if (attr_err != cudaSuccess) return set_error((int)attr_err, "lv_space_attn_bwd_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err));
+  const long long grid = p.num_groups < sm_count() ? p.num_groups : sm_count();
+  attn_tc::space_attn_bwd_tc_kernel<<<(unsigned)grid, attn_tc::NTHREADS, attn_tc::BWD_SMEM, (cudaStream_t)stream>>>(tm_qkv, tm_do, p);
+  return check_launch("lv_space_attn_bwd_tc");
+}

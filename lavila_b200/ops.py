@@ -71,13 +71,32 @@ def layernorm_bwd(dy, x, gamma, eps, rows, D, *, ldx=None, lddy=None, add1=None,
     L.check(rc, "lv_layernorm_bwd")
 
 
+USE_TC_ATTN_FWD = True   # tcgen05 space attention (TSF-B geometry); the mma.sync kernels cover every other shape
+USE_TC_ATTN_BWD = True
+
+
+def space_attn_tc_supported(n):
+    return 128 < n <= 207
+
+
 def group_attn_fwd(qkv, out, lse, mode, B, H, T=0, n=0, Lctx=0):
+    if mode == 0 and space_attn_tc_supported(n) and USE_TC_ATTN_FWD:   # tcgen05 path for TSF-B geometry
+        rc = L.lib().lv_space_attn_fwd_tc(qkv.data_ptr(), qkv.stride(0), out.data_ptr(), out.stride(0), lse.data_ptr(), B,
+                                          H, T, n, _stream())
+        L.check(rc, "lv_space_attn_fwd_tc")
+        return
     rc = L.lib().lv_group_attn_fwd(qkv.data_ptr(), qkv.stride(0), out.data_ptr(), out.stride(0), lse.data_ptr(), mode,
                                    B, H, T, n, Lctx, _stream())
     L.check(rc, "lv_group_attn_fwd")
 
 
 def group_attn_bwd(qkv, out, lse, dout, dqkv, dcls_kv, accumulate_kv, mode, B, H, T=0, n=0, Lctx=0):
+    if mode == 0 and space_attn_tc_supported(n) and USE_TC_ATTN_BWD:
+        rc = L.lib().lv_space_attn_bwd_tc(qkv.data_ptr(), qkv.stride(0), out.data_ptr(), out.stride(0), lse.data_ptr(),
+                                          dout.data_ptr(), dout.stride(0), dqkv.data_ptr(), dqkv.stride(0),
+                                          dcls_kv.data_ptr(), accumulate_kv, B, H, T, n, _stream())
+        L.check(rc, "lv_space_attn_bwd_tc")
+        return
     rc = L.lib().lv_group_attn_bwd(qkv.data_ptr(), qkv.stride(0), out.data_ptr(), out.stride(0), lse.data_ptr(),
                                    dout.data_ptr(), dout.stride(0), dqkv.data_ptr(), dqkv.stride(0), _p(dcls_kv),
                                    accumulate_kv, mode, B, H, T, n, Lctx, _stream())
