@@ -142,7 +142,8 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=240))
     import lavila_b200
     from lavila_b200 import _lib, engine, ops
     from lavila_b200.models import models as M
@@ -219,10 +220,10 @@ def run_ours(args):
                "d2h_bytes_per_step": 4 * world}
 
     roof = None
-    if not args.no_roofline and rank == 0:
+    if not args.no_roofline:
+        # every rank runs the instrumented steps (DDP's gradient all-reduce is collective); rank 0 reports its own GEMMs
         roof = gemm_roofline(lambda: step(frames_d, text_d), ops, torch)
-    if world > 1:
-        dist.barrier()
+    barrier()
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
