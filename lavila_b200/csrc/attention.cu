@@ -50,6 +50,8 @@ struct Params {
   long long ld_dqkv;
   float* dcls_kv;             // [B, H, 2, 64] fp32 (CLS key/value gradient accumulator)
   int accumulate_kv;          // add to the k/v gradient already in dqkv (written by the CLS-query backward)
+  int staged;                 // small groups: O and the old k/v gradient are staged in shared memory by cp.async
+  int group_bytes;            // shared-memory bytes per group (backward)
 };
 
 __device__ __forceinline__ uint32_t swz(int row, int chunk) { return row * ROW_BYTES + ((chunk ^ (row & 7)) << 4); }
@@ -260,7 +262,7 @@ __device__ __forceinline__ int bwd_group_bytes(int q_rows, int k_rows) {
 // the CLS key row goes to the fp32 accumulator with atomics at full precision.
 __device__ __forceinline__ void write_kv_grad(const Params& p, const GroupCoord& gc, float (&acc)[8][4], int part,
                                               int cls_slot, uint32_t sV, int kt, int key0, int key1, int lane, int t,
-                                              bool active) {
+                                              bool active, uint32_t sOld, float* cls_red) {
   __syncwarp();
 #pragma unroll
   for (int dt = 0; dt < 8; ++dt) {
@@ -268,14 +270,15 @@ __device__ __forceinline__ void write_kv_grad(const Params& p, const GroupCoord&
     st_shared_u32(sV + swz(key1, dt) + 4 * t, pack_bf16x2(acc[dt][2], acc[dt][3]));
   }
   if (active && p.has_cls && p.dcls_kv) {
-    float* base = p.dcls_kv + (((long long)gc.b * p.H + gc.h) * 2 + cls_slot) * HD;
+    // CLS key row: full-precision fp32; staged per group in shared memory, reduced per CTA before the global atomics
+    float* base = cls_red + cls_slot * HD;
     if (key0 == p.Lq) {
 #pragma unroll
-      for (int dt = 0; dt < 8; ++dt) { atomicAdd(base + dt * 8 + 2 * t, acc[dt][0]); atomicAdd(base + dt * 8 + 2 * t + 1, acc[dt][1]); }
+      for (int dt = 0; dt < 8; ++dt) { base[dt * 8 + 2 * t] = acc[dt][0]; base[dt * 8 + 2 * t + 1] = acc[dt][1]; }
     }
     if (key1 == p.Lq) {
 #pragma unroll
-      for (int dt = 0; dt < 8; ++dt) { atomicAdd(base + dt * 8 + 2 * t, acc[dt][2]); atomicAdd(base + dt * 8 + 2 * t + 1, acc[dt][3]); }
+      for (int dt = 0; dt < 8; ++dt) { base[dt * 8 + 2 * t] = acc[dt][2]; base[dt * 8 + 2 * t + 1] = acc[dt][3]; }
     }
   }
   __syncwarp();
@@ -288,7 +291,7 @@ __device__ __forceinline__ void write_kv_grad(const Params& p, const GroupCoord&
         uint4 v = ld_shared_v4(sV + swz(key, c));
         __nv_bfloat16* dst = p.dqkv + (gc.base_row + (long long)key * p.row_stride) * p.ld_dqkv + part * p.D + gc.h * HD + c * 8;
         if (p.accumulate_kv) {
-          const uint4 old = *reinterpret_cast<const uint4*>(dst);
+          const uint4 old = sOld ? ld_shared_v4(sOld + swz(key, c)) : *reinterpret_cast<const uint4*>(dst);
           uint32_t vw[4] = {v.x, v.y, v.z, v.w};
           const uint32_t ow[4] = {old.x, old.y, old.z, old.w};
 #pragma unroll
@@ -313,9 +316,15 @@ group_attn_bwd_kernel(const Params p, const int k_rows) {
   const bool active = group < p.num_groups;
   const int q_rows = p.qt * 16;
   const int ds_pitch = (q_rows + 8) * 2;  // bytes
-  const uint32_t gs = smem_u32(smem) + g_local * bwd_group_bytes(q_rows, k_rows);
+  const uint32_t gs = smem_u32(smem) + g_local * p.group_bytes;
   const uint32_t sQ = gs, sdO = sQ + q_rows * ROW_BYTES, sK = sdO + q_rows * ROW_BYTES, sV = sK + k_rows * ROW_BYTES;
   const uint32_t sLse = sV + k_rows * ROW_BYTES, sDelta = sLse + q_rows * 4, sdS = sDelta + q_rows * 4;
+  // small groups (time attention): O and the k/v gradient to accumulate onto are staged by the same cp.async batch,
+  // so no global-load latency is exposed after the MMAs
+  const bool staged = p.staged != 0;
+  const uint32_t sO = sdS + k_rows * ds_pitch;
+  const uint32_t sOldK = sO + q_rows * ROW_BYTES, sOldV = sOldK + k_rows * ROW_BYTES;
+  float* cls_red = reinterpret_cast<float*>(smem + p.groups_per_cta * p.group_bytes) + g_local * 2 * HD;
   float* lse_s = reinterpret_cast<float*>(smem + (sLse - smem_u32(smem)));
   float* delta_s = reinterpret_cast<float*>(smem + (sDelta - smem_u32(smem)));
   const GroupCoord gc = decode_group(p, active ? group : 0);
@@ -329,32 +338,61 @@ group_attn_bwd_kernel(const Params p, const int k_rows) {
     load_tile(sdO, q_rows, p.Lq, p.dout + gc.h * HD, p.ld_dout, gc.base_row, p.row_stride, nullptr, tid, nthr, active);
     load_tile(sK, k_rows, p.Lq, qb + p.D, p.ld_qkv, gc.base_row, p.row_stride, cls_k, tid, nthr, active);
     load_tile(sV, k_rows, p.Lq, qb + 2 * p.D, p.ld_qkv, gc.base_row, p.row_stride, cls_v, tid, nthr, active);
-    // delta_q = sum_d dO[q,d] * O[q,d]  (8 consecutive lanes share a row) and lse
-    for (int idx = tid; idx < q_rows * 8; idx += nthr) {
-      const int r = idx >> 3, c = idx & 7;
-      float part = 0.f;
-      if (active && r < p.Lq) {
-        const long long grow = gc.base_row + (long long)r * p.row_stride;
-        const uint4 a = __ldg(reinterpret_cast<const uint4*>(p.dout + grow * p.ld_dout + gc.h * HD + c * 8));
-        const uint4 b = __ldg(reinterpret_cast<const uint4*>(p.out + grow * p.ld_out + gc.h * HD + c * 8));
-        const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float2 x = unpack_bf16x2(aw[j]), y = unpack_bf16x2(bw[j]);
-          part += x.x * y.x + x.y * y.y;
-        }
+    if (staged) {
+      load_tile(sO, q_rows, p.Lq, p.out + gc.h * HD, p.ld_out, gc.base_row, p.row_stride, nullptr, tid, nthr, active);
+      if (p.accumulate_kv) {
+        const __nv_bfloat16* db = p.dqkv + gc.h * HD;
+        load_tile(sOldK, k_rows, p.Lq, db + p.D, p.ld_dqkv, gc.base_row, p.row_stride, nullptr, tid, nthr, active);
+        load_tile(sOldV, k_rows, p.Lq, db + 2 * p.D, p.ld_dqkv, gc.base_row, p.row_stride, nullptr, tid, nthr, active);
       }
-      part += __shfl_xor_sync(0xffffffffu, part, 1);
-      part += __shfl_xor_sync(0xffffffffu, part, 2);
-      part += __shfl_xor_sync(0xffffffffu, part, 4);
-      if (c == 0) {
-        delta_s[r] = part;
+      for (int r = tid; r < q_rows; r += nthr)
         lse_s[r] = (active && r < p.Lq) ? p.lse[(gc.base_row + (long long)r * p.row_stride) * p.H + gc.h] * LOG2E : 0.f;
+    } else {
+      // delta_q = sum_d dO[q,d] * O[q,d]  (8 consecutive lanes share a row) and lse, straight from global memory
+      for (int idx = tid; idx < q_rows * 8; idx += nthr) {
+        const int r = idx >> 3, c = idx & 7;
+        float part = 0.f;
+        if (active && r < p.Lq) {
+          const long long grow = gc.base_row + (long long)r * p.row_stride;
+          const uint4 a = __ldg(reinterpret_cast<const uint4*>(p.dout + grow * p.ld_dout + gc.h * HD + c * 8));
+          const uint4 b = __ldg(reinterpret_cast<const uint4*>(p.out + grow * p.ld_out + gc.h * HD + c * 8));
+          const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 x = unpack_bf16x2(aw[j]), y = unpack_bf16x2(bw[j]);
+            part += x.x * y.x + x.y * y.y;
+          }
+        }
+        part += __shfl_xor_sync(0xffffffffu, part, 1);
+        part += __shfl_xor_sync(0xffffffffu, part, 2);
+        part += __shfl_xor_sync(0xffffffffu, part, 4);
+        if (c == 0) {
+          delta_s[r] = part;
+          lse_s[r] = (active && r < p.Lq) ? p.lse[(gc.base_row + (long long)r * p.row_stride) * p.H + gc.h] * LOG2E : 0.f;
+        }
       }
     }
   }
   cp_async_wait_all();
   __syncthreads();
+  if (staged) {   // delta from the staged O and dO tiles
+    for (int idx = tid; idx < q_rows * 8; idx += nthr) {
+      const int r = idx >> 3, c = idx & 7;
+      const uint4 a = ld_shared_v4(sdO + swz(r, c)), b = ld_shared_v4(sO + swz(r, c));
+      const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+      float part = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 x = unpack_bf16x2(aw[j]), y = unpack_bf16x2(bw[j]);
+        part += x.x * y.x + x.y * y.y;
+      }
+      part += __shfl_xor_sync(0xffffffffu, part, 1);
+      part += __shfl_xor_sync(0xffffffffu, part, 2);
+      part += __shfl_xor_sync(0xffffffffu, part, 4);
+      if (c == 0) delta_s[r] = part;
+    }
+    __syncthreads();
+  }
 
   const int g = lane >> 2, t = lane & 3;
   const float sl2 = p.scale * LOG2E;
@@ -440,8 +478,8 @@ group_attn_bwd_kernel(const Params p, const int k_rows) {
       }
     }
     // ---- write dV then dK for this key tile; staging buffer = this warp's (private) V tile rows
-    write_kv_grad(p, gc, dv, /*part=*/2, /*cls_slot=*/1, sV, kt, key0, key1, lane, t, active);
-    write_kv_grad(p, gc, dk, /*part=*/1, /*cls_slot=*/0, sV, kt, key0, key1, lane, t, active);
+    write_kv_grad(p, gc, dv, /*part=*/2, /*cls_slot=*/1, sV, kt, key0, key1, lane, t, active, (staged && p.accumulate_kv) ? sOldV : 0u, cls_red);
+    write_kv_grad(p, gc, dk, /*part=*/1, /*cls_slot=*/0, sV, kt, key0, key1, lane, t, active, (staged && p.accumulate_kv) ? sOldK : 0u, cls_red);
   }
   __syncthreads();
   // ------------------------------------------------------------ phase 2: query tiles -> dQ = dS K
@@ -479,6 +517,27 @@ group_attn_bwd_kernel(const Params p, const int k_rows) {
           *reinterpret_cast<uint4*>(p.dqkv + (gc.base_row + (long long)qrow * p.row_stride) * p.ld_dqkv + gc.h * HD + c * 8) = v;
         }
       }
+    }
+  }
+  // ------------------------------------------------------------ CLS key/value gradient: per-CTA reduction, then atomics
+  if (p.has_cls && p.dcls_kv) {
+    __syncthreads();
+    const float* red_all = reinterpret_cast<const float*>(smem + p.groups_per_cta * p.group_bytes);
+    for (int e = threadIdx.x; e < 2 * HD; e += blockDim.x) {
+      float run = 0.f;
+      long long run_bh = -1;
+      for (int gl = 0; gl < p.groups_per_cta; ++gl) {
+        const long long gi = (long long)blockIdx.x * p.groups_per_cta + gl;
+        if (gi >= p.num_groups) break;
+        const long long bh = gi / p.inner;
+        if (bh != run_bh) {
+          if (run_bh >= 0) atomicAdd(p.dcls_kv + run_bh * 2 * HD + e, run);
+          run = 0.f;
+          run_bh = bh;
+        }
+        run += red_all[gl * 2 * HD + e];
+      }
+      if (run_bh >= 0) atomicAdd(p.dcls_kv + run_bh * 2 * HD + e, run);
     }
   }
 }
@@ -711,16 +770,19 @@ extern "C" int lv_group_attn_bwd(const void* qkv, int64_t ld_qkv, const void* ou
   const int Lk = p.Lq + p.has_cls;
   const int k_rows = (Lk + 15) / 16 * 16;
   const int q_rows = p.qt * 16;
-  const int per_group = 2 * q_rows * attn::ROW_BYTES + 2 * k_rows * attn::ROW_BYTES + 2 * q_rows * 4 + k_rows * (q_rows + 8) * 2;
-  LV_REQUIRE(per_group <= 227 * 1024, "lv_group_attn_bwd: group with %d keys does not fit in shared memory", Lk);
+  int per_group = 2 * q_rows * attn::ROW_BYTES + 2 * k_rows * attn::ROW_BYTES + 2 * q_rows * 4 + k_rows * (q_rows + 8) * 2;
+  p.staged = q_rows <= 32 ? 1 : 0;
+  if (p.staged) per_group += q_rows * attn::ROW_BYTES + 2 * k_rows * attn::ROW_BYTES;
+  p.group_bytes = per_group;
+  LV_REQUIRE(per_group + 512 <= 227 * 1024, "lv_group_attn_bwd: group with %d keys does not fit in shared memory", Lk);
   int wg = (k_rows / 16 + 1) / 2;
   if (wg > 8) wg = 8;
   if (wg < 1) wg = 1;
   int gpc = 8 / wg;
-  while (gpc > 1 && gpc * per_group > 112 * 1024) gpc >>= 1;
+  while (gpc > 1 && gpc * (per_group + 512) > 113 * 1024) gpc >>= 1;
   p.wg = wg;
   p.groups_per_cta = gpc;
-  const int smem = gpc * per_group;
+  const int smem = gpc * (per_group + 2 * attn::HD * 4);
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(attn::group_attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);

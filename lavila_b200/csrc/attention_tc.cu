@@ -27,7 +27,7 @@ constexpr int SQ_BYTES = QROWS * 128;
 constexpr int SK_BYTES = KROWS * 128;
 constexpr int SP_BYTES = 4 * 128 * 128;  // P tile: 4 atoms of (128 rows x 64 keys)
 constexpr int NTHREADS = 320;
-constexpr int TM_S = 0, TM_O = 2 * KROWS;  // TMEM columns: S0 [0,208) S1 [208,416) O [416,480)
+constexpr int TM_S = 0;  // TMEM columns: S0 [0,208), S1 [208,416); O_t overwrites the first 64 columns of S_t
 constexpr int TMEM_COLS = 512;
 constexpr float LOG2E = 1.4426950408889634f;
 
@@ -80,12 +80,13 @@ space_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const Param
   uint8_t* sV = sK + SK_BYTES;
   uint8_t* sP = sV + SK_BYTES;  // two tiles
   uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * SP_BYTES);
-  uint64_t* bar_load = bars;
+  uint64_t* bar_load = bars;       // Q + K landed
   uint64_t* bar_s = bars + 1;
   uint64_t* bar_p = bars + 2;      // [2]
   uint64_t* bar_o = bars + 4;      // [2]
   uint64_t* bar_ofree = bars + 6;  // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* bar_loadv = bars + 8;  // V landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int Lq = p.n, Lk = p.n + 1;
@@ -93,6 +94,7 @@ space_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const Param
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tm_qkv);
     mbar_init(bar_load, 1);
+    mbar_init(bar_loadv, 1);
     mbar_init(bar_s, 1);
     for (int t = 0; t < 2; ++t) {
       mbar_init(&bar_p[t], 4);
@@ -120,26 +122,39 @@ space_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const Param
 
   if (warp == 0) {
     // ------------------------------------------------------------------ producer
+    // Q and K of group i+1 are requested as soon as the S MMAs of group i have retired (they overlap the softmax),
+    // V of group i+1 once the last P.V MMA of group i has read V.
     int it = 0;
     for (long long g = blockIdx.x; g < p.num_groups; g += gridDim.x, ++it) {
+      const Coord c = decode(p, g);
       if (it > 0) {
-        if (lane == 0) mbar_wait(&bar_o[1], (it - 1) & 1);  // previous group's last MMA has read Q, K, V
+        if (lane == 0) mbar_wait(bar_s, (it - 1) & 1);
         __syncwarp();
       }
-      const Coord c = decode(p, g);
-      if (lane < 16) {  // CLS key / value row -> row Lq of the K / V tiles (generic proxy, swizzled by hand)
-        const int part = lane >> 3, ch = lane & 7;
-        const uint4 v = __ldg(reinterpret_cast<const uint4*>(p.qkv + c.cls_row * p.ld_qkv + (1 + part) * p.D + c.h * HD + ch * 8));
-        const uint32_t dst = smem_u32(part ? sV : sK) + Lq * 128 + ((ch ^ (Lq & 7)) << 4);
-        st_shared_v4(dst, v.x, v.y, v.z, v.w);
+      if (lane < 8) {  // CLS key row -> row Lq of the K tile (generic proxy, swizzled by hand)
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(p.qkv + c.cls_row * p.ld_qkv + p.D + c.h * HD + lane * 8));
+        st_shared_v4(smem_u32(sK) + Lq * 128 + ((lane ^ (Lq & 7)) << 4), v.x, v.y, v.z, v.w);
       }
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) {
-        mbar_arrive_expect_tx(bar_load, 3 * Lq * 128);
+        mbar_arrive_expect_tx(bar_load, 2 * Lq * 128);
         tma_load_2d(sQ, &tm_qkv, bar_load, c.h * HD, (int)c.base_row);
         tma_load_2d(sK, &tm_qkv, bar_load, p.D + c.h * HD, (int)c.base_row);
-        tma_load_2d(sV, &tm_qkv, bar_load, 2 * p.D + c.h * HD, (int)c.base_row);
+      }
+      if (it > 0) {
+        if (lane == 0) mbar_wait(&bar_o[1], (it - 1) & 1);
+        __syncwarp();
+      }
+      if (lane < 8) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(p.qkv + c.cls_row * p.ld_qkv + 2 * p.D + c.h * HD + lane * 8));
+        st_shared_v4(smem_u32(sV) + Lq * 128 + ((lane ^ (Lq & 7)) << 4), v.x, v.y, v.z, v.w);
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive_expect_tx(bar_loadv, Lq * 128);
+        tma_load_2d(sV, &tm_qkv, bar_loadv, 2 * p.D + c.h * HD, (int)c.base_row);
       }
     }
   } else if (warp == 1) {
@@ -152,6 +167,10 @@ space_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const Param
       for (long long g = blockIdx.x; g < p.num_groups; g += gridDim.x, ++it) {
         const uint32_t ph = it & 1;
         mbar_wait(bar_load, ph);
+        if (it > 0) {  // O_t lives in the first 64 columns of S_t: both must have been drained by the epilogue warps
+          mbar_wait(&bar_ofree[0], (it - 1) & 1);
+          mbar_wait(&bar_ofree[1], (it - 1) & 1);
+        }
         tc_fence_after();
 #pragma unroll
         for (int t = 0; t < 2; ++t)
@@ -160,16 +179,14 @@ space_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const Param
             tc_mma_bf16(tmem_base + TM_S + t * KROWS, make_smem_desc_sw128(q_base + t * 16384 + ks * 32, 16, 1024),
                         make_smem_desc_sw128(k_base + ks * 32, 16, 1024), idesc_s, ks > 0);
         tc_commit(bar_s);
+        mbar_wait(bar_loadv, ph);
 #pragma unroll 1
         for (int t = 0; t < 2; ++t) {
-          mbar_wait(&bar_p[t], ph);
-          // the single O accumulator must have been drained by the previous user
-          if (t == 0) { if (it > 0) mbar_wait(&bar_ofree[1], (it - 1) & 1); }
-          else mbar_wait(&bar_ofree[0], ph);
+          mbar_wait(&bar_p[t], ph);   // P_t staged; the softmax warps have finished reading S_t
           tc_fence_after();
 #pragma unroll
           for (int s = 0; s < KROWS / 16; ++s)
-            tc_mma_bf16(tmem_base + TM_O, make_smem_desc_sw128(p_base + t * SP_BYTES + (s >> 2) * 16384 + (s & 3) * 32, 16, 1024),
+            tc_mma_bf16(tmem_base + TM_S + t * KROWS, make_smem_desc_sw128(p_base + t * SP_BYTES + (s >> 2) * 16384 + (s & 3) * 32, 16, 1024),
                         make_smem_desc_sw128(v_base + s * 2048, 8192, 1024), idesc_o, s > 0);
           tc_commit(&bar_o[t]);
         }
@@ -197,9 +214,14 @@ space_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const Param
         uint32_t r[32];
         tmem_ld_32x32(ts + cc * 32, r);
         tmem_ld_wait();
+        if ((cc + 1) * 32 <= Lk) {   // interior chunk: no key masking
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (cc * 32 + j < Lk) m = fmaxf(m, __uint_as_float(r[j]));
+          for (int j = 0; j < 32; ++j) m = fmaxf(m, __uint_as_float(r[j]));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (cc * 32 + j < Lk) m = fmaxf(m, __uint_as_float(r[j]));
+        }
       }
       {
         uint32_t r[16];
@@ -218,10 +240,18 @@ space_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const Param
         tmem_ld_32x32(ts + cc * 32, r);
         tmem_ld_wait();
         float pv[32];
+        if ((cc + 1) * 32 <= Lk) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          pv[j] = (cc * 32 + j < Lk) ? exp2f(fmaf(__uint_as_float(r[j]), sl2, -mb)) : 0.f;
-          sum += pv[j];
+          for (int j = 0; j < 32; ++j) {
+            pv[j] = exp2f(fmaf(__uint_as_float(r[j]), sl2, -mb));
+            sum += pv[j];
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            pv[j] = (cc * 32 + j < Lk) ? exp2f(fmaf(__uint_as_float(r[j]), sl2, -mb)) : 0.f;
+            sum += pv[j];
+          }
         }
         const uint32_t atom = p_tile + (cc >> 1) * 16384;
 #pragma unroll
@@ -257,8 +287,8 @@ space_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const Param
       mbar_wait(&bar_o[t], ph);
       tc_fence_after();
       uint32_t o0[32], o1[32];
-      tmem_ld_32x32(trow + TM_O, o0);
-      tmem_ld_32x32(trow + TM_O + 32, o1);
+      tmem_ld_32x32(trow + TM_S + t * KROWS, o0);        // O_t aliases the first 64 columns of S_t
+      tmem_ld_32x32(trow + TM_S + t * KROWS + 32, o1);
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();

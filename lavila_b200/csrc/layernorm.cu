@@ -68,100 +68,105 @@ ln_fwd_kernel(const float* __restrict__ x, long long ldx, const float* __restric
 
 // Persistent: each warp walks rows with a grid stride, keeps dgamma/dbeta partials in registers, the CTA reduces
 // them through shared memory and issues one red.add per column.
-template <bool DY_BF16>
+// HBM-latency-bound unless enough bytes are in flight: NV (float4 per lane) is a compile-time constant so that ALL
+// global loads of R rows (x, dy, residual-path gradients) are issued back to back before the first use
+// (R = 2 rows per warp iteration with <= 1 residual operand, 1 row with 2: ~12-15 KB in flight per warp).
+template <int NV, int R, int NADD, bool DY_BF16>
 __global__ void __launch_bounds__(WARPS * 32)
 ln_bwd_kernel(const void* __restrict__ dy_, long long lddy, const float* __restrict__ x, long long ldx,
               const float* __restrict__ gamma, float eps, const float* __restrict__ add1, long long ld1,
               const float* __restrict__ add2, long long ld2, float* __restrict__ dx, long long lddx,
               __nv_bfloat16* __restrict__ dx_bf16, long long lddxb, float* __restrict__ dgamma,
-              float* __restrict__ dbeta, long long rows, int D) {
+              float* __restrict__ dbeta, long long rows) {
   extern __shared__ float red[];  // [WARPS][2][D]
+  constexpr int D = NV * 128;
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
-  const int nv = D >> 7;
-  float4 dg[MAX_V], db[MAX_V];
+  float4 dg[NV], db[NV];
 #pragma unroll
-  for (int i = 0; i < MAX_V; ++i) {
+  for (int i = 0; i < NV; ++i) {
     dg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     db[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
-  for (long long row = (long long)blockIdx.x * WARPS + warp; row < rows; row += (long long)gridDim.x * WARPS) {
-    const float* xr = x + row * ldx;
-    float4 xv[MAX_V], gv[MAX_V], av[MAX_V];
-    float s = 0.f;
-    // all global loads of the row are issued up front (x, dy, residual-path gradients): one exposed latency per row
+  const long long stride = (long long)gridDim.x * WARPS * R;
+  for (long long row0 = ((long long)blockIdx.x * WARPS + warp) * R; row0 < rows; row0 += stride) {
+    float4 xv[R][NV], gv[R][NV], a1v[R][NV], a2v[R][NV];
+    // ---- issue every load of the R rows
 #pragma unroll
-    for (int i = 0; i < MAX_V; ++i)
-      if (i < nv) {
-        const int col = (i * 32 + lane) * 4;
-        av[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (add1) av[i] = __ldg(reinterpret_cast<const float4*>(add1 + row * ld1 + col));
-        if (add2) {
-          const float4 a = __ldg(reinterpret_cast<const float4*>(add2 + row * ld2 + col));
-          av[i].x += a.x; av[i].y += a.y; av[i].z += a.z; av[i].w += a.w;
-        }
-      }
+    for (int r = 0; r < R; ++r) {
+      const long long row = row0 + r < rows ? row0 + r : rows - 1;   // tail: recompute the last row, store is masked
 #pragma unroll
-    for (int i = 0; i < MAX_V; ++i)
-      if (i < nv) {
+      for (int i = 0; i < NV; ++i) {
         const int col = (i * 32 + lane) * 4;
-        xv[i] = __ldg(reinterpret_cast<const float4*>(xr + col));
-        s += xv[i].x + xv[i].y + xv[i].z + xv[i].w;
+        xv[r][i] = __ldg(reinterpret_cast<const float4*>(x + row * ldx + col));
         if (DY_BF16) {
           const uint2 u = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(dy_) + row * lddy + col));
-          const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
-          gv[i] = make_float4(a.x, a.y, b.x, b.y);
+          gv[r][i] = make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xffff0000u),
+                                 __uint_as_float(u.y << 16), __uint_as_float(u.y & 0xffff0000u));
         } else {
-          gv[i] = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(dy_) + row * lddy + col));
+          gv[r][i] = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(dy_) + row * lddy + col));
+        }
+        if (NADD >= 1) a1v[r][i] = __ldg(reinterpret_cast<const float4*>(add1 + row * ld1 + col));
+        if (NADD >= 2) a2v[r][i] = __ldg(reinterpret_cast<const float4*>(add2 + row * ld2 + col));
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const long long row = row0 + r;
+      const bool live = row < rows;
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) s += xv[r][i].x + xv[r][i].y + xv[r][i].z + xv[r][i].w;
+      const float mean = warp_sum(s) / D;
+      float ss = 0.f;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        xv[r][i].x -= mean; xv[r][i].y -= mean; xv[r][i].z -= mean; xv[r][i].w -= mean;
+        ss += xv[r][i].x * xv[r][i].x + xv[r][i].y * xv[r][i].y + xv[r][i].z * xv[r][i].z + xv[r][i].w * xv[r][i].w;
+      }
+      const float rstd = rsqrtf(warp_sum(ss) / D + eps);
+      float c1 = 0.f, c2 = 0.f;
+      const float lv_ = live ? 1.f : 0.f;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        float4& xh = xv[r][i];
+        float4& g = gv[r][i];
+        xh.x *= rstd; xh.y *= rstd; xh.z *= rstd; xh.w *= rstd;  // xhat
+        dg[i].x += lv_ * g.x * xh.x; dg[i].y += lv_ * g.y * xh.y; dg[i].z += lv_ * g.z * xh.z; dg[i].w += lv_ * g.w * xh.w;
+        db[i].x += lv_ * g.x; db[i].y += lv_ * g.y; db[i].z += lv_ * g.z; db[i].w += lv_ * g.w;
+        const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma + (i * 32 + lane) * 4));  // L1-resident
+        g.x *= gm.x; g.y *= gm.y; g.z *= gm.z; g.w *= gm.w;  // dy * gamma
+        c1 += g.x + g.y + g.z + g.w;
+        c2 += g.x * xh.x + g.y * xh.y + g.z * xh.z + g.w * xh.w;
+      }
+      c1 = warp_sum(c1) / D;
+      c2 = warp_sum(c2) / D;
+      if (live) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+          const int col = (i * 32 + lane) * 4;
+          float4 o;
+          o.x = rstd * (gv[r][i].x - c1 - xv[r][i].x * c2);
+          o.y = rstd * (gv[r][i].y - c1 - xv[r][i].y * c2);
+          o.z = rstd * (gv[r][i].z - c1 - xv[r][i].z * c2);
+          o.w = rstd * (gv[r][i].w - c1 - xv[r][i].w * c2);
+          if (NADD >= 1) { o.x += a1v[r][i].x; o.y += a1v[r][i].y; o.z += a1v[r][i].z; o.w += a1v[r][i].w; }
+          if (NADD >= 2) { o.x += a2v[r][i].x; o.y += a2v[r][i].y; o.z += a2v[r][i].z; o.w += a2v[r][i].w; }
+          if (dx) *reinterpret_cast<float4*>(dx + row * lddx + col) = o;
+          if (dx_bf16)
+            *reinterpret_cast<uint2*>(dx_bf16 + row * lddxb + col) = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
         }
       }
-    const float mean = warp_sum(s) / D;
-    float ss = 0.f;
-#pragma unroll
-    for (int i = 0; i < MAX_V; ++i)
-      if (i < nv) {
-        xv[i].x -= mean; xv[i].y -= mean; xv[i].z -= mean; xv[i].w -= mean;
-        ss += xv[i].x * xv[i].x + xv[i].y * xv[i].y + xv[i].z * xv[i].z + xv[i].w * xv[i].w;
-      }
-    const float rstd = rsqrtf(warp_sum(ss) / D + eps);
-    float c1 = 0.f, c2 = 0.f;
-#pragma unroll
-    for (int i = 0; i < MAX_V; ++i)
-      if (i < nv) {
-        xv[i].x *= rstd; xv[i].y *= rstd; xv[i].z *= rstd; xv[i].w *= rstd;  // xhat
-        dg[i].x += gv[i].x * xv[i].x; dg[i].y += gv[i].y * xv[i].y; dg[i].z += gv[i].z * xv[i].z; dg[i].w += gv[i].w * xv[i].w;
-        db[i].x += gv[i].x; db[i].y += gv[i].y; db[i].z += gv[i].z; db[i].w += gv[i].w;
-        const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma + (i * 32 + lane) * 4));  // L1-resident
-        gv[i].x *= gm.x; gv[i].y *= gm.y; gv[i].z *= gm.z; gv[i].w *= gm.w;  // dy * gamma
-        c1 += gv[i].x + gv[i].y + gv[i].z + gv[i].w;
-        c2 += gv[i].x * xv[i].x + gv[i].y * xv[i].y + gv[i].z * xv[i].z + gv[i].w * xv[i].w;
-      }
-    c1 = warp_sum(c1) / D;
-    c2 = warp_sum(c2) / D;
-#pragma unroll
-    for (int i = 0; i < MAX_V; ++i)
-      if (i < nv) {
-        const int col = (i * 32 + lane) * 4;
-        float4 o;
-        o.x = rstd * (gv[i].x - c1 - xv[i].x * c2);
-        o.y = rstd * (gv[i].y - c1 - xv[i].y * c2);
-        o.z = rstd * (gv[i].z - c1 - xv[i].z * c2);
-        o.w = rstd * (gv[i].w - c1 - xv[i].w * c2);
-        o.x += av[i].x; o.y += av[i].y; o.z += av[i].z; o.w += av[i].w;
-        if (dx) *reinterpret_cast<float4*>(dx + row * lddx + col) = o;
-        if (dx_bf16)
-          *reinterpret_cast<uint2*>(dx_bf16 + row * lddxb + col) = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
-      }
+    }
   }
   if (!dgamma) return;
   float* rg = red + (size_t)warp * 2 * D;
 #pragma unroll
-  for (int i = 0; i < MAX_V; ++i)
-    if (i < nv) {
-      const int col = (i * 32 + lane) * 4;
-      *reinterpret_cast<float4*>(rg + col) = dg[i];
-      *reinterpret_cast<float4*>(rg + D + col) = db[i];
-    }
+  for (int i = 0; i < NV; ++i) {
+    const int col = (i * 32 + lane) * 4;
+    *reinterpret_cast<float4*>(rg + col) = dg[i];
+    *reinterpret_cast<float4*>(rg + D + col) = db[i];
+  }
   __syncthreads();
   for (int c = threadIdx.x; c < 2 * D; c += blockDim.x) {
     float t = 0.f;
@@ -170,6 +175,36 @@ ln_bwd_kernel(const void* __restrict__ dy_, long long lddy, const float* __restr
     if (c < D) red_add_f32(dgamma + c, t);
     else red_add_f32(dbeta + (c - D), t);
   }
+}
+
+template <int NV, int R, int NADD, bool DY_BF16>
+static int launch_ln_bwd(const void* dy, long long lddy, const float* x, long long ldx, const float* gamma, float eps,
+                         const float* add1, long long ld1, const float* add2, long long ld2, float* dx, long long lddx,
+                         void* dx_bf16, long long lddxb, float* dgamma, float* dbeta, long long rows, cudaStream_t st) {
+  constexpr int D = NV * 128;
+  const size_t smem = (size_t)WARPS * 2 * D * sizeof(float);
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(ln_bwd_kernel<NV, R, NADD, DY_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    configured = true;
+  }
+  long long want = (rows + WARPS * R - 1) / (WARPS * R);
+  long long cap = (long long)sm_count() * 4;
+  const unsigned grid = (unsigned)(want < cap ? want : cap);
+  ln_bwd_kernel<NV, R, NADD, DY_BF16><<<grid, WARPS * 32, smem, st>>>(dy, lddy, x, ldx, gamma, eps, add1, ld1, add2, ld2, dx,
+                                                                      lddx, (__nv_bfloat16*)dx_bf16, lddxb, dgamma, dbeta, rows);
+  return check_launch("lv_layernorm_bwd");
+}
+
+template <int NV, bool DY_BF16>
+static int dispatch_ln_bwd(int nadd, const void* dy, long long lddy, const float* x, long long ldx, const float* gamma,
+                           float eps, const float* add1, long long ld1, const float* add2, long long ld2, float* dx,
+                           long long lddx, void* dx_bf16, long long lddxb, float* dgamma, float* dbeta, long long rows,
+                           cudaStream_t st) {
+  constexpr int R01 = NV <= 6 ? 2 : 1;   // two rows in flight while registers allow
+  if (nadd == 0) return launch_ln_bwd<NV, R01, 0, DY_BF16>(dy, lddy, x, ldx, gamma, eps, add1, ld1, add2, ld2, dx, lddx, dx_bf16, lddxb, dgamma, dbeta, rows, st);
+  if (nadd == 1) return launch_ln_bwd<NV, R01, 1, DY_BF16>(dy, lddy, x, ldx, gamma, eps, add1, ld1, add2, ld2, dx, lddx, dx_bf16, lddxb, dgamma, dbeta, rows, st);
+  return launch_ln_bwd<NV, 1, 2, DY_BF16>(dy, lddy, x, ldx, gamma, eps, add1, ld1, add2, ld2, dx, lddx, dx_bf16, lddxb, dgamma, dbeta, rows, st);
 }
 
 }  // namespace ln
@@ -200,22 +235,21 @@ extern "C" int lv_layernorm_bwd(const void* dy, int dy_is_bf16, int64_t lddy, co
   LV_REQUIRE(lddy % 4 == 0 && ldx % 4 == 0 && ld1 % 4 == 0 && ld2 % 4 == 0 && lddx % 4 == 0 && lddxb % 4 == 0,
              "lv_layernorm_bwd: leading dimensions must be multiples of 4");
   if (rows <= 0) return 0;
-  long long want = (rows + ln::WARPS - 1) / ln::WARPS;
-  long long cap = (long long)sm_count() * 4;
-  const unsigned grid = (unsigned)(want < cap ? want : cap);
-  const size_t smem = (size_t)ln::WARPS * 2 * D * sizeof(float);
+  LV_REQUIRE(!(add2 && !add1), "lv_layernorm_bwd: add2 without add1");
+  const int nadd = add1 ? (add2 ? 2 : 1) : 0;
   cudaStream_t st = (cudaStream_t)stream;
-  static bool configured = false;
-  if (!configured) {  // D = 1024 needs 64 KB of dynamic shared memory for the dgamma/dbeta reduction
-    cudaFuncSetAttribute(ln::ln_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-    cudaFuncSetAttribute(ln::ln_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-    configured = true;
+#define LV_LN_BWD(NV)                                                                                                      \
+  return dy_is_bf16 ? ln::dispatch_ln_bwd<NV, true>(nadd, dy, lddy, x, ldx, gamma, eps, add1, ld1, add2, ld2, dx, lddx,      \
+                                                    dx_bf16, lddxb, dgamma, dbeta, rows, st)                                \
+                    : ln::dispatch_ln_bwd<NV, false>(nadd, dy, lddy, x, ldx, gamma, eps, add1, ld1, add2, ld2, dx, lddx,     \
+                                                     dx_bf16, lddxb, dgamma, dbeta, rows, st)
+  switch (D / 128) {
+    case 1: LV_LN_BWD(1);
+    case 2: LV_LN_BWD(2);
+    case 4: LV_LN_BWD(4);
+    case 6: LV_LN_BWD(6);
+    case 8: LV_LN_BWD(8);
+    default: return set_error(-1, "lv_layernorm_bwd: D=%d not instantiated (128, 256, 512, 768, 1024)", D);
   }
-  if (dy_is_bf16)
-    ln::ln_bwd_kernel<true><<<grid, ln::WARPS * 32, smem, st>>>(dy, lddy, x, ldx, gamma, eps, add1, ld1, add2, ld2, dx, lddx,
-                                                                (__nv_bfloat16*)dx_bf16, lddxb, dgamma, dbeta, rows, D);
-  else
-    ln::ln_bwd_kernel<false><<<grid, ln::WARPS * 32, smem, st>>>(dy, lddy, x, ldx, gamma, eps, add1, ld1, add2, ld2, dx, lddx,
-                                                                 (__nv_bfloat16*)dx_bf16, lddxb, dgamma, dbeta, rows, D);
-  return check_launch("lv_layernorm_bwd");
+#undef LV_LN_BWD
 }
