@@ -569,28 +569,45 @@ space_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __gri
         const int ncols = qt ? 40 : 64;         // this warp's share of the query columns
         const int col_base = hf * ncols;
         const uint32_t pt_row = smem_u32(sPt) + row * 128, ds_row = smem_u32(sdSt) + row * 128;
-        for (int cb = 0; cb < ncols; cb += 8) {
+        // 32 columns per TMEM round trip (one wait per 32x2 values instead of per 8)
+        for (int cb = 0; cb < ncols; cb += 32) {
           const int col0 = col_base + cb;       // query column inside the tile
-          uint32_t s8[8], d8[8];
-          tmem_ld_32x8(trow + TB_ST + col0, s8);
-          tmem_ld_32x8(trow + TB_DPT + col0, d8);
-          tmem_ld_wait();
-          const int qg = qt * 128 + col0;
-          const float4 la = *reinterpret_cast<const float4*>(s_lse + qg), lb = *reinterpret_cast<const float4*>(s_lse + qg + 4);
-          const float4 da = *reinterpret_cast<const float4*>(s_delta + qg), db = *reinterpret_cast<const float4*>(s_delta + qg + 4);
-          const float l8[8] = {la.x, la.y, la.z, la.w, lb.x, lb.y, lb.z, lb.w};
-          const float dl8[8] = {da.x, da.y, da.z, da.w, db.x, db.y, db.z, db.w};
-          float pv[8], dv[8];
+          uint32_t s32[32], d32[32];
+          const bool wide = cb + 32 <= ncols;   // qt = 1 ends with an 8-column remainder (40 = 32 + 8)
+          if (wide) {
+            tmem_ld_32x32(trow + TB_ST + col0, s32);
+            tmem_ld_32x32(trow + TB_DPT + col0, d32);
+          } else {
+            uint32_t s8[8], d8[8];
+            tmem_ld_32x8(trow + TB_ST + col0, s8);
+            tmem_ld_32x8(trow + TB_DPT + col0, d8);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const bool ok = key_ok && (qg + j < Lq);
-            const float pj = ok ? exp2f(fmaf(__uint_as_float(s8[j]), sl2, -l8[j])) : 0.f;
-            pv[j] = pj;
-            dv[j] = pj * (__uint_as_float(d8[j]) - dl8[j]) * p.scale;
+            for (int j = 0; j < 8; ++j) { s32[j] = s8[j]; d32[j] = d8[j]; }
           }
-          const uint32_t off = (col0 >> 6) * 16384 + ((((col0 & 63) >> 3) ^ (row & 7)) << 4);
-          st_shared_v4(pt_row + off, pack_bf16x2(pv[0], pv[1]), pack_bf16x2(pv[2], pv[3]), pack_bf16x2(pv[4], pv[5]), pack_bf16x2(pv[6], pv[7]));
-          st_shared_v4(ds_row + off, pack_bf16x2(dv[0], dv[1]), pack_bf16x2(dv[2], dv[3]), pack_bf16x2(dv[4], dv[5]), pack_bf16x2(dv[6], dv[7]));
+          tmem_ld_wait();
+          const int ngroups = wide ? 4 : 1;
+#pragma unroll
+          for (int g8 = 0; g8 < 4; ++g8) {
+            if (g8 < ngroups) {
+              const int c8 = col0 + g8 * 8;
+              const int qg = qt * 128 + c8;
+              const float4 la = *reinterpret_cast<const float4*>(s_lse + qg), lb = *reinterpret_cast<const float4*>(s_lse + qg + 4);
+              const float4 da = *reinterpret_cast<const float4*>(s_delta + qg), db = *reinterpret_cast<const float4*>(s_delta + qg + 4);
+              const float l8[8] = {la.x, la.y, la.z, la.w, lb.x, lb.y, lb.z, lb.w};
+              const float dl8[8] = {da.x, da.y, da.z, da.w, db.x, db.y, db.z, db.w};
+              float pv[8], dv[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const bool ok = key_ok && (qg + j < Lq);
+                const float pj = ok ? exp2f(fmaf(__uint_as_float(s32[g8 * 8 + j]), sl2, -l8[j])) : 0.f;
+                pv[j] = pj;
+                dv[j] = pj * (__uint_as_float(d32[g8 * 8 + j]) - dl8[j]) * p.scale;
+              }
+              const uint32_t off = (c8 >> 6) * 16384 + ((((c8 & 63) >> 3) ^ (row & 7)) << 4);
+              st_shared_v4(pt_row + off, pack_bf16x2(pv[0], pv[1]), pack_bf16x2(pv[2], pv[3]), pack_bf16x2(pv[4], pv[5]), pack_bf16x2(pv[6], pv[7]));
+              st_shared_v4(ds_row + off, pack_bf16x2(dv[0], dv[1]), pack_bf16x2(dv[2], dv[3]), pack_bf16x2(dv[4], dv[5]), pack_bf16x2(dv[6], dv[7]));
+            }
+          }
         }
         fence_proxy_async_smem();
         tc_fence_before();
