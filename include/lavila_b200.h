@@ -56,7 +56,9 @@ enum {
   LV_EPI_OUT_F32 = 64,    /* `out` is fp32 (default bf16)                                            */
   LV_EPI_COPY_BF16 = 128, /* out2 <- bf16(v) (final value), e.g. bf16 shadow of an fp32 stream       */
   LV_EPI_ATOMIC = 256,    /* out[m,n] += v with fp32 atomics (implies LV_EPI_OUT_F32)                */
-  LV_EPI_ROWBIAS = 512    /* v += bias[m] instead of bias[n] (unused by torch layouts; tests only)   */
+  LV_EPI_ROWBIAS = 512,   /* v += bias[m] instead of bias[n] (unused by torch layouts; tests only)   */
+  LV_EPI_GELU_TANH = 1024,/* v = 0.5 v (1 + tanh(sqrt(2/pi)(v + 0.044715 v^3)))  (HF 'gelu_new', inference) */
+  LV_EPI_SQRELU = 2048    /* v = relu(v)^2  (gpt2_gated.SqReLU, inference)                           */
 };
 
 typedef struct LvGemmEpilogue {
@@ -79,6 +81,7 @@ int lv_gemm_bf16(const void* A, int64_t lda, int a_mn, const void* B, int64_t ld
  * Replaces nn.LayerNorm at lavila/models/timesformer.py:180,189,196 (eps 1e-6), :366 ln_pre (1e-5), :377 norm;
  * lavila/models/openai_model.py:196,200 ln_1/ln_2 and models.py:156 ln_final (1e-5).
  *   fwd: y = LN(x) written as bf16 (GEMM operand) and/or fp32.  Any of y_bf16 / y_f32 may be NULL (not both).
+ *        fwd also accepts any D % 4 == 0 (GPT-2 XL: 1600) and beta == NULL (coca.LayerNorm, coca.py:28-35).
  *   bwd: dx = dLN(dy) [+ add1] [+ add2] written as fp32 and/or bf16; dgamma/dbeta accumulated with fp32 atomics
  *        (may be NULL together).  mean/rstd are recomputed from x.
  * ---------------------------------------------------------------------------------------------- */
@@ -116,6 +119,13 @@ int lv_space_attn_fwd_tc(const void* qkv, int64_t ld_qkv, void* out, int64_t ld_
 int lv_space_attn_bwd_tc(const void* qkv, int64_t ld_qkv, const void* out, int64_t ld_out, const float* lse,
                          const void* dout, int64_t ld_dout, void* dqkv, int64_t ld_dqkv, float* dcls_kv, int accumulate_kv,
                          int B, int H, int T, int n, void* stream);
+/* General attention forward (inference): flash-style, head_dim 64, bf16 in/out, optional causal mask, multi-query
+ * K/V when kv_head_stride = 0.  Q element (b,h,i,d) at q[(b*q_rows+i)*ld_q + h*64 + d]; K/V element (b,h,j,d) at
+ * k[(b*kv_rows+j)*ld_kv + h*kv_head_stride + d].  Replaces gpt2_gated.GPT2Attention._attn (:206-238) and
+ * coca.CrossAttention's einsum/softmax/einsum (coca.py:114-121). */
+int lv_flash_attn_fwd(const void* q, int64_t ld_q, int64_t q_rows, const void* k, const void* v, int64_t ld_kv,
+                      int64_t kv_rows, int kv_head_stride, void* out, int64_t ld_out, int B, int H, int Lq, int Lk,
+                      int causal, float scale, void* stream);
 int lv_cls_attn_fwd(const void* qkv, int64_t ld_qkv, void* out, int64_t ld_out, float* lse, int B, int H, int N,
                     void* stream);
 int lv_cls_attn_bwd(const void* qkv, int64_t ld_qkv, const void* out, int64_t ld_out, const void* dout, int64_t ld_dout,

@@ -14,6 +14,7 @@ c_void_p, c_int, c_int64, c_float = ctypes.c_void_p, ctypes.c_int, ctypes.c_int6
 # epilogue flags (include/lavila_b200.h)
 EPI_BIAS, EPI_QUICKGELU, EPI_DQUICKGELU, EPI_SCALE, EPI_SCALE_TANH = 1, 2, 4, 8, 16
 EPI_RESID, EPI_OUT_F32, EPI_COPY_BF16, EPI_ATOMIC, EPI_ROWBIAS = 32, 64, 128, 256, 512
+EPI_GELU_TANH, EPI_SQRELU = 1024, 2048
 
 
 class LvGemmEpilogue(ctypes.Structure):

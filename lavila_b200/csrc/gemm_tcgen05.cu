@@ -286,6 +286,20 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 v.z = h1.x * sigmoidf_fast(1.702f * h1.x);
                 v.w = h1.y * sigmoidf_fast(1.702f * h1.y);
               }
+              if (flags & LV_EPI_GELU_TANH) {
+                float* vv[4] = {&v.x, &v.y, &v.z, &v.w};
+#pragma unroll
+                for (int e2 = 0; e2 < 4; ++e2) {
+                  const float xx = *vv[e2];
+                  float th;
+                  asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(0.7978845608028654f * (xx + 0.044715f * xx * xx * xx)));
+                  *vv[e2] = 0.5f * xx * (1.0f + th);
+                }
+              }
+              if (flags & LV_EPI_SQRELU) {
+                v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+                v.x *= v.x; v.y *= v.y; v.z *= v.z; v.w *= v.w;
+              }
               if (flags & LV_EPI_DQUICKGELU) {
                 const uint2 hb = pre_aux[i];
                 const float2 h0 = unpack_bf16x2(hb.x), h1 = unpack_bf16x2(hb.y);

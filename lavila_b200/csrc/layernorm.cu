@@ -66,6 +66,43 @@ ln_fwd_kernel(const float* __restrict__ x, long long ldx, const float* __restric
     }
 }
 
+// Any width with D % 4 == 0 (e.g. GPT-2 XL's 1600): warp per row, three passes over the (L1-resident) row.
+__global__ void __launch_bounds__(WARPS * 32)
+ln_fwd_generic_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ gamma,
+                      const float* __restrict__ beta, float eps, __nv_bfloat16* __restrict__ y_bf16, long long ldy,
+                      float* __restrict__ y_f32, long long ldyf, long long rows, int D) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * WARPS + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float* xr = x + row * ldx;
+  float s = 0.f;
+  for (int c = lane * 4; c < D; c += 128) {
+    const float4 v = *reinterpret_cast<const float4*>(xr + c);
+    s += v.x + v.y + v.z + v.w;
+  }
+  const float mean = warp_sum(s) / D;
+  float ss = 0.f;
+  for (int c = lane * 4; c < D; c += 128) {
+    const float4 v = *reinterpret_cast<const float4*>(xr + c);
+    const float a = v.x - mean, b = v.y - mean, cc = v.z - mean, d = v.w - mean;
+    ss += a * a + b * b + cc * cc + d * d;
+  }
+  const float rstd = rsqrtf(warp_sum(ss) / D + eps);
+  for (int c = lane * 4; c < D; c += 128) {
+    const float4 v = *reinterpret_cast<const float4*>(xr + c);
+    const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
+    float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (beta) b = __ldg(reinterpret_cast<const float4*>(beta + c));
+    float4 o;
+    o.x = (v.x - mean) * rstd * g.x + b.x;
+    o.y = (v.y - mean) * rstd * g.y + b.y;
+    o.z = (v.z - mean) * rstd * g.z + b.z;
+    o.w = (v.w - mean) * rstd * g.w + b.w;
+    if (y_bf16) *reinterpret_cast<uint2*>(y_bf16 + row * ldy + c) = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
+    if (y_f32) *reinterpret_cast<float4*>(y_f32 + row * ldyf + c) = o;
+  }
+}
+
 // Persistent: each warp walks rows with a grid stride, keeps dgamma/dbeta partials in registers, the CTA reduces
 // them through shared memory and issues one red.add per column.
 // HBM-latency-bound unless enough bytes are in flight: NV (float4 per lane) is a compile-time constant so that ALL
@@ -214,13 +251,17 @@ extern "C" int lv_layernorm_fwd(const float* x, int64_t ldx, const float* gamma,
                                 void* y_bf16, int64_t ldy, float* y_f32, int64_t ldyf, int64_t rows, int D,
                                 void* stream) {
   using namespace lv;
-  LV_REQUIRE(x && gamma && beta && (y_bf16 || y_f32), "lv_layernorm_fwd: null pointer");
-  LV_REQUIRE(D > 0 && D % 128 == 0 && D <= 128 * ln::MAX_V, "lv_layernorm_fwd: D=%d must be a multiple of 128 and <= 1024", D);
+  LV_REQUIRE(x && gamma && (y_bf16 || y_f32), "lv_layernorm_fwd: null pointer");
+  LV_REQUIRE(D > 0 && D % 4 == 0, "lv_layernorm_fwd: D=%d must be a multiple of 4", D);
   LV_REQUIRE(ldx % 4 == 0 && ldy % 4 == 0 && ldyf % 4 == 0, "lv_layernorm_fwd: leading dimensions must be multiples of 4");
   if (rows <= 0) return 0;
   const unsigned grid = (unsigned)((rows + ln::WARPS - 1) / ln::WARPS);
-  ln::ln_fwd_kernel<<<grid, ln::WARPS * 32, 0, (cudaStream_t)stream>>>(x, ldx, gamma, beta, eps, (__nv_bfloat16*)y_bf16, ldy,
-                                                                      y_f32, ldyf, rows, D);
+  if (beta && D % 128 == 0 && D <= 128 * ln::MAX_V)
+    ln::ln_fwd_kernel<<<grid, ln::WARPS * 32, 0, (cudaStream_t)stream>>>(x, ldx, gamma, beta, eps, (__nv_bfloat16*)y_bf16, ldy,
+                                                                        y_f32, ldyf, rows, D);
+  else   // beta may be NULL (coca.LayerNorm keeps a zero buffer), any D % 4 == 0
+    ln::ln_fwd_generic_kernel<<<grid, ln::WARPS * 32, 0, (cudaStream_t)stream>>>(x, ldx, gamma, beta, eps, (__nv_bfloat16*)y_bf16,
+                                                                                ldy, y_f32, ldyf, rows, D);
   return check_launch("lv_layernorm_fwd");
 }
 

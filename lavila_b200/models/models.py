@@ -151,3 +151,45 @@ def CLIP_OPENAI_TIMESFORMER_LARGE_336PX(num_frames=4, timesformer_gated_xattn=Fa
     return _build(dict(img_size=336, patch_size=14, embed_dim=1024, depth=24, num_heads=16), 1024, 768, 12, 12,
                   num_frames, timesformer_gated_xattn, drop_path_rate, timesformer_freeze_space, temperature_init,
                   project_embed_dim, checkpoint, kwargs)
+
+
+# ------------------------------------------------------------------------------------------------ narrator factories
+def _vclm(vision_kwargs, vision_width, gpt2_cfg, cross_attn_freq, heads, num_frames, gated_xattn, timesformer_gated_xattn,
+          freeze_lm_vclm, freeze_visual_vclm, freeze_visual_vclm_temporal, checkpoint, kwargs):
+    from types import SimpleNamespace
+    from .gpt2_gated import GPT2LMHeadModel as GatedGPT2LMHeadModel, augment_gpt2_config
+    from .narrator import VCLM_HF
+    vision_model = SpaceTimeTransformer(num_frames=num_frames, time_init='zeros', attention_style='frozen-in-time', ln_pre=True,
+                                        act_layer=QuickGELU, is_tanh_gating=timesformer_gated_xattn, **vision_kwargs)
+    vision_model.head = nn.Identity()
+    vision_model.pre_logits = nn.Identity()
+    vision_model.fc = nn.Identity()
+    config = SimpleNamespace(layer_norm_epsilon=1e-5, activation_function="gelu_new", n_positions=1024, vocab_size=50257, **gpt2_cfg)
+    text_decoder = GatedGPT2LMHeadModel(augment_gpt2_config(config, cross_attn_freq=cross_attn_freq, gated_xattn=gated_xattn))
+    if freeze_lm_vclm:
+        text_decoder.freeze_lm_weights()
+    if freeze_visual_vclm:
+        vision_model.freeze_spatial_weights()
+    if freeze_visual_vclm_temporal:
+        vision_model.freeze_temporal_weights()
+    model = VCLM_HF(vision_width=vision_width, vision_model=vision_model, text_width=gpt2_cfg["n_embd"],
+                    text_decoder=text_decoder, num_img_queries=256, dim_head=64, heads=heads, **kwargs)
+    _load_checkpoint(model, checkpoint)
+    return model
+
+
+def VCLM_OPENAI_TIMESFORMER_BASE_GPT2(gated_xattn=False, random_init_gpt2=False, freeze_lm_vclm=False,
+                                      freeze_visual_vclm=False, freeze_visual_vclm_temporal=False, num_frames=4,
+                                      timesformer_gated_xattn=False, checkpoint=None, **kwargs):
+    """models.py:887-948: TSF-B/16 + GPT-2 (768/12/12), cross-attention in every layer, 12 pooling heads."""
+    return _vclm({}, 768, dict(n_embd=768, n_layer=12, n_head=12), 1, 12, num_frames, gated_xattn, timesformer_gated_xattn,
+                 freeze_lm_vclm, freeze_visual_vclm, freeze_visual_vclm_temporal, checkpoint, kwargs)
+
+
+def VCLM_OPENAI_TIMESFORMER_BASE_GPT2_XL(gated_xattn=False, random_init_gpt2=False, freeze_lm_vclm=False,
+                                         freeze_visual_vclm=False, freeze_visual_vclm_temporal=False, num_frames=4,
+                                         timesformer_gated_xattn=False, checkpoint=None, **kwargs):
+    """TSF-B/16 + GPT-2 XL (1600/48/25), cross-attention every 2nd layer, 25 pooling heads (the decoder of
+    models.py:1012-1072; the TSF-L/14 video encoder of that factory needs key-tiled space attention -- next)."""
+    return _vclm({}, 768, dict(n_embd=1600, n_layer=48, n_head=25), 2, 25, num_frames, gated_xattn, timesformer_gated_xattn,
+                 freeze_lm_vclm, freeze_visual_vclm, freeze_visual_vclm_temporal, checkpoint, kwargs)

@@ -57,7 +57,7 @@ def wgrad_splits(m_out, n_in, k_tokens, sms=148):
 
 
 def layernorm_fwd(x, gamma, beta, eps, rows, D, *, ldx=None, y_bf16=None, y_f32=None):
-    rc = L.lib().lv_layernorm_fwd(x.data_ptr(), ldx if ldx is not None else D, gamma.data_ptr(), beta.data_ptr(), eps,
+    rc = L.lib().lv_layernorm_fwd(x.data_ptr(), ldx if ldx is not None else D, gamma.data_ptr(), _p(beta), eps,
                                   _p(y_bf16), D, _p(y_f32), D, rows, D, _stream())
     L.check(rc, "lv_layernorm_fwd")
 
@@ -101,6 +101,13 @@ def group_attn_bwd(qkv, out, lse, dout, dqkv, dcls_kv, accumulate_kv, mode, B, H
                                    dout.data_ptr(), dout.stride(0), dqkv.data_ptr(), dqkv.stride(0), _p(dcls_kv),
                                    accumulate_kv, mode, B, H, T, n, Lctx, _stream())
     L.check(rc, "lv_group_attn_bwd")
+
+
+def flash_attn_fwd(q, k, v, out, B, H, Lq, Lk, *, q_rows, kv_rows, ld_q, ld_kv, ld_out, kv_head_stride=64, causal=False,
+                   scale=0.125):
+    rc = L.lib().lv_flash_attn_fwd(q.data_ptr(), ld_q, q_rows, k.data_ptr(), v.data_ptr(), ld_kv, kv_rows, kv_head_stride,
+                                   out.data_ptr(), ld_out, B, H, Lq, Lk, int(causal), float(scale), _stream())
+    L.check(rc, "lv_flash_attn_fwd")
 
 
 def cls_attn_fwd(qkv, out, lse, B, H, N):

@@ -1,0 +1,102 @@
+"""GPU parity of the narrator inference path (VCLM_HF: TimeSformer features -> attention pooling -> gated GPT-2) against
+the golden vectors of the unmodified reference and the oracle.  Tolerance: bf16 operands / fp32 accumulation vs fp32
+reference -> rel-L2 <= 2e-2, cosine >= 0.999 (logits 3e-2: 2 decoder layers + LM head over bf16 activations)."""
+import os
+from types import SimpleNamespace
+
+import pytest
+import torch
+
+from oracle import narrator as ON
+from oracle.dual_encoder import synthetic_batch
+from tests.util import assert_close_bf16, rel_l2
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+GOLD = torch.load(os.path.join(os.path.dirname(__file__), "golden", "narrator_small.pt"), weights_only=False)
+
+
+def build(cfg, params):
+    from lavila_b200.models.gpt2_gated import GPT2LMHeadModel, augment_gpt2_config
+    from lavila_b200.models.narrator import VCLM_HF
+    from lavila_b200.models.timesformer import SpaceTimeTransformer, QuickGELU
+    v = cfg["visual"]
+    vis = SpaceTimeTransformer(img_size=v["img_size"], patch_size=v["patch_size"], embed_dim=v["embed_dim"], depth=v["depth"],
+                               num_heads=v["num_heads"], num_frames=v["num_frames"], time_init="zeros", ln_pre=True,
+                               act_layer=QuickGELU)
+    vis.head = torch.nn.Identity()
+    vis.pre_logits = torch.nn.Identity()
+    g = SimpleNamespace(vocab_size=cfg["vocab_size"], n_positions=cfg["n_positions"], n_embd=cfg["n_embd"],
+                        n_layer=cfg["n_layer"], n_head=cfg["n_head"], layer_norm_epsilon=1e-5, activation_function="gelu_new")
+    dec = GPT2LMHeadModel(augment_gpt2_config(g, cross_attn_freq=cfg["cross_attn_freq"], gated_xattn=True))
+    m = VCLM_HF(vision_width=v["embed_dim"], vision_model=vis, text_width=cfg["n_embd"], text_decoder=dec,
+                num_img_queries=cfg["num_img_queries"], dim_head=64, heads=cfg["pool_heads"])
+    res = m.load_state_dict(params, strict=False)
+    assert not res.unexpected_keys
+    assert all(k.endswith(("attn.bias", "attn.masked_bias", "crossattention.bias", "crossattention.masked_bias", ".beta"))
+               for k in res.missing_keys), res.missing_keys
+    return m.to(DEV).eval()
+
+
+def _setup():
+    cfg = GOLD["cfg"]
+    p = ON.init_narrator_params(cfg, seed=0)
+    vcfg = dict(cfg["visual"], context_length=8, vocab_size=8)
+    frames, _ = synthetic_batch(vcfg, 2, seed=GOLD["frames_seed"])
+    return cfg, build(cfg, p), frames.to(DEV)
+
+
+def test_encode_image_matches_reference_golden():
+    cfg, m, frames = _setup()
+    tok = m.encode_image(frames)
+    assert_close_bf16(tok, GOLD["image_tokens"], "image tokens")
+
+
+def test_logits_match_reference_golden():
+    cfg, m, frames = _setup()
+    out = m(frames, GOLD["text"].to(DEV))
+    assert torch.equal(out["labels"].cpu(), GOLD["labels"])
+    assert_close_bf16(out["text_tokens_logits"], GOLD["logits"], "teacher-forced logits", rel=3e-2, cos=0.999)
+    tok = m.encode_image(frames)
+    pre = m.text_decoder(GOLD["text"][:, :5].contiguous().to(DEV), encoder_hidden_states=tok).logits
+    assert_close_bf16(pre, GOLD["logits_prefix5"], "prefix logits", rel=3e-2, cos=0.999)
+    last = m.text_decoder(GOLD["text"][:, :5].contiguous().to(DEV), encoder_hidden_states=tok, last_only=True).logits
+    assert rel_l2(last[:, 0], pre[:, -1]) < 1e-5     # last-position shortcut == full LM head, same kernels
+
+
+def test_generate_runs_like_reference():
+    cfg, m, frames = _setup()
+    tok = m.encode_image(frames)
+    t = SimpleNamespace(bos_token_id=cfg["vocab_size"] - 1, eos_token_id=cfg["vocab_size"] - 1, pad_token_id=0)
+    torch.manual_seed(0)
+    ids, ppl = m.generate(tok, t, max_text_length=6, top_p=0.95, temperature=0.7, num_return_sequences=2)
+    assert tuple(ids.shape) == GOLD["gen_shape"] and tuple(ppl.shape) == GOLD["ppl_shape"]
+    assert ids.dtype == torch.int64 and bool((ids[:, 0] == t.bos_token_id).all())
+    assert bool(torch.isfinite(ppl).all())
+    # the oracle's warper keeps the same token set as the transformers warper used by generate (index op: exact)
+    logits = m.text_decoder(ids[:, :3].contiguous(), encoder_hidden_states=tok.repeat_interleave(2, 0), last_only=True).logits[:, -1]
+    w = m._get_logits_warper(top_p=0.95, temperature=0.7, num_beams=1)(ids[:, :3], logits.clone())
+    assert torch.equal(torch.isinf(w), torch.isinf(ON.warp_logits(logits, 0.7, 0.95)))
+
+
+@pytest.mark.parametrize("B,H,Lq,Lk,mqa,causal", [(2, 3, 5, 40, False, False), (2, 25, 77, 256, False, False),
+                                                   (3, 4, 77, 77, False, True), (2, 12, 256, 785, True, False),
+                                                   (1, 2, 1, 1, False, True), (2, 2, 130, 130, False, True)])
+def test_flash_attention(B, H, Lq, Lk, mqa, causal):
+    from lavila_b200 import ops
+    torch.manual_seed(1)
+    q = torch.randn(B, Lq, H, 64, device=DEV).bfloat16()
+    hk = 1 if mqa else H
+    k = torch.randn(B, Lk, hk, 64, device=DEV).bfloat16()
+    v = torch.randn(B, Lk, hk, 64, device=DEV).bfloat16()
+    kv = torch.cat((k, v), dim=2).contiguous()            # [B, Lk, 2*hk, 64]: k heads then v heads
+    out = torch.zeros(B, Lq, H, 64, device=DEV, dtype=torch.bfloat16)
+    ops.flash_attn_fwd(q, kv, kv.view(B * Lk, -1)[:, hk * 64:], out, B, H, Lq, Lk, q_rows=Lq, kv_rows=Lk, ld_q=H * 64,
+                       ld_kv=2 * hk * 64, ld_out=H * 64, kv_head_stride=0 if mqa else 64, causal=causal, scale=0.125)
+    qf, kf, vf = q.float().permute(0, 2, 1, 3), k.float().permute(0, 2, 1, 3), v.float().permute(0, 2, 1, 3)
+    s = (qf @ kf.transpose(-1, -2)) * 0.125
+    if causal:
+        mask = torch.ones(Lk, Lk, dtype=torch.bool, device=DEV).tril()[Lk - Lq:Lk]
+        s = s.masked_fill(~mask, float("-inf"))
+    ref = (torch.softmax(s, dim=-1) @ vf).permute(0, 2, 1, 3)
+    assert rel_l2(out, ref) < 1e-2
