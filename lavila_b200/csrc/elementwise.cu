@@ -322,7 +322,7 @@ extern "C" int lv_embed_assemble_bwd(const float* dx0, float* dpos, float* dcls,
 
 extern "C" int lv_text_embed(const int64_t* text, const float* tok, const float* pos, float* x, int64_t rows, int L, int W,
                              int vocab, void* stream) {
-  LV_REQUIRE(text && tok && pos && x && W % 128 == 0, "lv_text_embed: bad arguments");
+  LV_REQUIRE(text && tok && pos && x && W % 4 == 0, "lv_text_embed: bad arguments (W must be a multiple of 4)");
   ew::text_embed_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>((const long long*)text, tok, pos, x, rows, L, W, vocab);
   return check_launch("lv_text_embed");
 }

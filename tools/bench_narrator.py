@@ -1,0 +1,78 @@
+"""Narrator inference throughput (BASELINE.json config 4 shape, TSF-B video encoder + gated GPT-2 XL decoder, random
+weights): encode_image + generate(top_p=0.95, temperature=0.7, max_text_length=77, early_stopping=False).
+
+    python tools/bench_narrator.py --batch 32 --returns 1 [--impl eager]   # eager = oracle port on the GPU (fp32)
+"""
+import argparse
+import json
+import os
+import sys
+import time
+from types import SimpleNamespace
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--batch", type=int, default=32)
+    ap.add_argument("--returns", type=int, default=1)
+    ap.add_argument("--frames", type=int, default=4)
+    ap.add_argument("--max-len", type=int, default=77)
+    ap.add_argument("--impl", default="ours", choices=["ours", "eager"])
+    ap.add_argument("--decoder", default="xl", choices=["xl", "base"])
+    a = ap.parse_args()
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(0)
+    tok = SimpleNamespace(bos_token_id=50256, eos_token_id=50256, pad_token_id=0)
+    frames = torch.randn(a.batch, 3, a.frames, 224, 224, device=dev)
+    if a.impl == "ours":
+        from lavila_b200.models import models as M
+        f = M.VCLM_OPENAI_TIMESFORMER_BASE_GPT2_XL if a.decoder == "xl" else M.VCLM_OPENAI_TIMESFORMER_BASE_GPT2
+        model = f(gated_xattn=True, num_frames=a.frames).to(dev).eval()
+        with torch.no_grad():
+            for n, p in model.named_parameters():
+                if "alpha" in n:
+                    p.fill_(0.5)
+                if "timeattn" in n or "temporal_embed" in n:
+                    p.normal_(0, 0.02)
+
+        def run():
+            t = model.encode_image(frames)
+            return model.generate(t, tok, max_text_length=a.max_len, top_p=0.95, temperature=0.7,
+                                  num_return_sequences=a.returns, early_stopping=False)
+    else:
+        from oracle import narrator as ON
+        H, Ld, nh, freq = (1600, 48, 25, 2) if a.decoder == "xl" else (768, 12, 12, 1)
+        cfg = dict(visual=dict(img_size=224, patch_size=16, embed_dim=768, depth=12, num_heads=12, num_frames=a.frames, ln_pre=True),
+                   n_embd=H, n_head=nh, n_layer=Ld, cross_attn_freq=freq, vocab_size=50257, n_positions=1024,
+                   num_img_queries=256, pool_heads=nh)
+        p = {k: v.to(dev) for k, v in ON.init_narrator_params(cfg, seed=0).items()}
+        # oracle helpers build zeros on the CPU: make default tensors land on the GPU for this arm
+        torch.set_default_device(dev)
+
+        def run():   # the reference algorithm: no caches, full re-forward and full LM head every step
+            with torch.no_grad():
+                t = ON.vclm_encode_image(frames, p, cfg).repeat_interleave(a.returns, 0)
+                ids = torch.full((t.shape[0], 1), 50256, dtype=torch.int64, device=dev)
+                for _ in range(a.max_len - 1):
+                    lg = ON.gpt2_lm_logits(ids, t, p, cfg)[:, -1]
+                    pr = torch.softmax(ON.warp_logits(lg, 0.7, 0.95), dim=-1)
+                    ids = torch.cat((ids, torch.multinomial(pr, 1)), 1)
+                return ids, None
+    run()
+    torch.cuda.synchronize()
+    t0 = time.time()
+    ids, _ = run()
+    torch.cuda.synchronize()
+    dt = time.time() - t0
+    print(json.dumps({"impl": a.impl, "decoder": a.decoder, "batch": a.batch, "returns": a.returns, "frames": a.frames,
+                      "tokens": int(ids.shape[1]), "seconds": round(dt, 3), "clips_per_s": round(a.batch / dt, 3),
+                      "sequences_per_s": round(a.batch * a.returns / dt, 3),
+                      "max_mem_gb": round(torch.cuda.max_memory_allocated() / 2 ** 30, 1)}))
+
+
+if __name__ == "__main__":
+    main()
