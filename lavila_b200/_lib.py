@@ -43,6 +43,8 @@ def _declare(lib):
     lib.lv_gemm_bf16.restype = c_int
     lib.lv_gemm_bf16.argtypes = [c_void_p, c_int64, c_int, c_void_p, c_int64, c_int, c_int64, c_int64, c_int64, c_int,
                                  ctypes.POINTER(LvGemmEpilogue), c_void_p]
+    lib.lv_gemm_bf16_2cta.restype = c_int
+    lib.lv_gemm_bf16_2cta.argtypes = lib.lv_gemm_bf16.argtypes
     from . import _decl  # remaining entry points
     _decl.declare(lib)
 

@@ -1,0 +1,340 @@
+// 2-CTA ("cta_group::2") variant of the persistent bf16 GEMM: a cluster of two CTAs on one TPC computes a 256 x 256
+// output tile.  Each CTA TMA-loads its own 128 rows of A and HALF of the B tile (128 of the 256 N rows); one
+// tcgen05.mma.cta_group::2 issued by the leader CTA drives both SMs' tensor cores (M = 256), each reading the other
+// CTA's B half through the pair.  Per SM and k-block this moves 32 KB into shared memory and reads 32 KB out of it
+// (1-CTA 128x256 tiles: 48 + 48 KB) -- the shared-memory pipe, not the tensor pipe, bounds the 1-CTA kernel
+// (profiles/ncu_r01_fwd_b16_summary.txt).
+//
+// Synchronisation (per CTA unless noted):
+//   full[s]   (leader only) : leader arrives with expect_tx(2 x 32 KB); BOTH CTAs' TMA loads complete_tx on it
+//                             (barrier address with the peer bit cleared, `.cta_group::2` TMA)
+//   empty[s]                : tcgen05.commit.cta_group::2 ... multicast -> arrives in both CTAs when the MMAs that read
+//                             stage s have retired
+//   tfull[a]                : multicast commit after the last k-block of a tile
+//   tempty[a] (leader only) : the 2 x 8 epilogue warps of the pair arrive remotely (mapa + mbarrier.arrive.shared::cluster)
+// Same operand layouts, epilogues and C ABI as gemm_tcgen05.cu.
+#include <mutex>
+
+#include "../../include/lavila_b200.h"
+#include "gemm_epilogue.cuh"
+#include "host_common.h"
+#include "ptx.cuh"
+
+namespace lv {
+namespace gemm2 {
+
+using gemm::Args;
+using gemm::BN;
+using gemm::EPI_PITCH;
+
+constexpr int BM_CTA = 128;   // rows per CTA; the pair covers 256
+constexpr int BN_CTA = 128;   // B rows (N) loaded per CTA
+constexpr int BK = 64;
+constexpr int STAGES = 6;
+constexpr int UMMA_K = 16;
+constexpr int A_STAGE_BYTES = BM_CTA * BK * 2;   // 16 KB
+constexpr int B_STAGE_BYTES = BN_CTA * BK * 2;   // 16 KB
+constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+constexpr int ATOM_BYTES = 64 * BK * 2;
+constexpr int EPI_WARPS = 8;
+constexpr int EPI_BYTES = EPI_WARPS * 32 * EPI_PITCH * 4;
+constexpr int NUM_BARS = 2 * STAGES + 4;
+constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + EPI_BYTES + NUM_BARS * 8 + 16;
+static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS;
+constexpr int TMEM_COLS = 512;
+constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t* smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish2() { asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// TMA load executed by either CTA of the pair; completes transaction bytes on the LEADER's barrier.
+__device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* tmap, uint64_t* bar, int32_t c0, int32_t c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(smem_u32(bar) & PEER_MASK), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_mma2_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive (once the MMAs issued so far have retired) on the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void tc_commit2(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) {
+  asm volatile(
+      "{\n"
+      ".reg .b32 ra;\n"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(cta)
+      : "memory");
+}
+
+template <int A_MN, int B_MN, int CT_FLAGS>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Args g) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * A_STAGE_BYTES;
+  float* sEpi = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + EPI_BYTES);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + STAGES;
+  uint64_t* tfull_bar = bars + 2 * STAGES;
+  uint64_t* tempty_bar = bars + 2 * STAGES + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + NUM_BARS);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull_bar[a], 1);
+      mbar_init(&tempty_bar[a], 2 * EPI_WARPS);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc2(tmem_slot, TMEM_COLS);
+    tmem_relinquish2();
+  }
+  tc_fence_before();
+  cluster_sync_all();   // barriers of both CTAs initialised, TMEM of both allocated
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int n_tiles = g.num_m_blks * g.num_n_blks;     // num_m_blks counts 256-row tiles
+  const int total_items = n_tiles * g.k_splits;
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer (both CTAs)
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int item = cluster_id; item < total_items; item += num_clusters) {
+        const int split = item / n_tiles;
+        const int tile = item - split * n_tiles;
+        const int m_blk = tile / g.num_n_blks;
+        const int n_blk = tile - m_blk * g.num_n_blks;
+        const int kb0 = split * g.kb_per_split;
+        const int kb1 = min(g.num_kb, kb0 + g.kb_per_split);
+        const int m0 = m_blk * 256 + rank * BM_CTA;
+        const int n0 = n_blk * BN + rank * BN_CTA;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * STAGE_BYTES);
+          const int k0 = kb * BK;
+          uint8_t* a_dst = sA + stage * A_STAGE_BYTES;
+          uint8_t* b_dst = sB + stage * B_STAGE_BYTES;
+          if (A_MN) {
+#pragma unroll
+            for (int j = 0; j < BM_CTA / 64; ++j) tma_load_2d_2sm(a_dst + j * ATOM_BYTES, &tmA, &full_bar[stage], m0 + j * 64, k0);
+          } else {
+            tma_load_2d_2sm(a_dst, &tmA, &full_bar[stage], k0, m0);
+          }
+          if (B_MN) {
+#pragma unroll
+            for (int j = 0; j < BN_CTA / 64; ++j) tma_load_2d_2sm(b_dst + j * ATOM_BYTES, &tmB, &full_bar[stage], n0 + j * 64, k0);
+          } else {
+            tma_load_2d_2sm(b_dst, &tmB, &full_bar[stage], k0, n0);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA only)
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(256, BN, A_MN, B_MN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int item = cluster_id; item < total_items; item += num_clusters, ++it) {
+        const int split = item / n_tiles;
+        const int kb0 = split * g.kb_per_split;
+        const int kb1 = min(g.num_kb, kb0 + g.kb_per_split);
+        const int as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        mbar_wait(&tempty_bar[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(sA + stage * A_STAGE_BYTES);
+          const uint32_t b_base = smem_u32(sB + stage * B_STAGE_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            const uint64_t adesc = A_MN ? make_smem_desc_sw128(a_base + k * UMMA_K * 128, ATOM_BYTES, 1024)
+                                        : make_smem_desc_sw128(a_base + k * UMMA_K * 2, 16, 1024);
+            const uint64_t bdesc = B_MN ? make_smem_desc_sw128(b_base + k * UMMA_K * 128, ATOM_BYTES, 1024)
+                                        : make_smem_desc_sw128(b_base + k * UMMA_K * 2, 16, 1024);
+            tc_mma2_bf16(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          tc_commit2(&empty_bar[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        tc_commit2(&tfull_bar[as]);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue warps (both CTAs, own 128 rows)
+    const int q = warp & 3;
+    const int e = warp - 2;
+    const int half = e >> 2;
+    float* buf = sEpi + e * 32 * EPI_PITCH;
+    const int flags = CT_FLAGS >= 0 ? CT_FLAGS : g.flags;
+    float scale = 1.0f;
+    if (flags & LV_EPI_SCALE) {
+      scale = __ldg(g.scale_ptr);
+      if (flags & LV_EPI_SCALE_TANH) scale = tanhf(scale);
+    }
+    int it = 0;
+    for (int item = cluster_id; item < total_items; item += num_clusters, ++it) {
+      const int split = item / n_tiles;
+      const int tile = item - split * n_tiles;
+      const int m_blk = tile / g.num_n_blks;
+      const int n_blk = tile - m_blk * g.num_n_blks;
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      gemm::epilogue_tile<CT_FLAGS>(g, flags, scale, buf, &tfull_bar[as], aphase, tmem_base + as * BN,
+                                    m_blk * 256 + (int)rank * BM_CTA + q * 32, n_blk * BN, half, q, lane);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote(&tempty_bar[as], 0);   // the leader's MMA warp owns the accumulator hand-off
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();   // neither CTA may exit (or free TMEM) while its peer can still touch its smem / barriers
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc2(tmem_base, TMEM_COLS);
+  }
+}
+
+template <int A_MN, int B_MN, int CT_FLAGS>
+static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const Args& g, cudaStream_t stream) {
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, []() {
+    attr_err = cudaFuncSetAttribute(gemm2_bf16_kernel<A_MN, B_MN, CT_FLAGS>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+  });
+  if (attr_err != cudaSuccess) return set_error((int)attr_err, "gemm2: cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err));
+  const int total = g.num_m_blks * g.num_n_blks * g.k_splits;
+  int clusters = sm_count() / 2;
+  if (total < clusters) clusters = total;
+  gemm2_bf16_kernel<A_MN, B_MN, CT_FLAGS><<<2 * clusters, NUM_THREADS, SMEM_BYTES, stream>>>(tmA, tmB, g);
+  return check_launch("lv_gemm_bf16 (2-CTA)");
+}
+
+template <int A_MN, int B_MN, int F>
+static int try_spec(bool& hit, const CUtensorMap& tmA, const CUtensorMap& tmB, const Args& g, cudaStream_t st) {
+  if constexpr (gemm::is_specialised(A_MN, B_MN, F)) {
+    if (!hit && g.flags == F) { hit = true; return launch<A_MN, B_MN, F>(tmA, tmB, g, st); }
+  }
+  return 0;
+}
+
+template <int A_MN, int B_MN>
+static int dispatch(const CUtensorMap& tmA, const CUtensorMap& tmB, const Args& g, cudaStream_t st) {
+  bool hit = false;
+  int rc = 0;
+#define LV_TRY(F) if (!hit) rc = try_spec<A_MN, B_MN, (F)>(hit, tmA, tmB, g, st);
+  LV_TRY(0)
+  LV_TRY(LV_EPI_BIAS)
+  LV_TRY(LV_EPI_BIAS | LV_EPI_QUICKGELU)
+  LV_TRY(LV_EPI_OUT_F32)
+  LV_TRY(LV_EPI_BIAS | LV_EPI_RESID | LV_EPI_OUT_F32)
+  LV_TRY(LV_EPI_BIAS | LV_EPI_SCALE | LV_EPI_SCALE_TANH | LV_EPI_RESID | LV_EPI_OUT_F32)
+  LV_TRY(LV_EPI_DQUICKGELU)
+  LV_TRY(LV_EPI_ATOMIC | LV_EPI_OUT_F32)
+#undef LV_TRY
+  if (hit) return rc;
+  return launch<A_MN, B_MN, -1>(tmA, tmB, g, st);
+}
+
+}  // namespace gemm2
+}  // namespace lv
+
+// Same contract as lv_gemm_bf16 (include/lavila_b200.h); 256 x 256 tiles computed by CTA pairs.
+extern "C" int lv_gemm_bf16_2cta(const void* A, int64_t lda, int a_mn, const void* B, int64_t ldb, int b_mn, int64_t M,
+                                 int64_t N, int64_t K, int k_splits, const LvGemmEpilogue* epi, void* stream) {
+  using namespace lv;
+  using namespace lv::gemm2;
+  LV_REQUIRE(A && B && epi && epi->out, "lv_gemm_bf16_2cta: null pointer");
+  LV_REQUIRE(M > 0 && N > 0 && K > 0 && M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), "lv_gemm_bf16_2cta: bad shape");
+  LV_REQUIRE((N & 3) == 0 && (epi->ldo & 3) == 0, "lv_gemm_bf16_2cta: N and ldo must be multiples of 4");
+  const int flags = epi->flags;
+  LV_REQUIRE(!(flags & LV_EPI_BIAS) || epi->bias, "lv_gemm_bf16_2cta: LV_EPI_BIAS without bias");
+  LV_REQUIRE(!(flags & LV_EPI_RESID) || (epi->resid && (epi->ldr & 3) == 0), "lv_gemm_bf16_2cta: bad resid");
+  LV_REQUIRE(!(flags & (LV_EPI_QUICKGELU | LV_EPI_COPY_BF16)) || (epi->out2 && (epi->ldo2 & 3) == 0), "lv_gemm_bf16_2cta: out2 required");
+  LV_REQUIRE(!(flags & LV_EPI_DQUICKGELU) || (epi->aux && (epi->ldaux & 3) == 0), "lv_gemm_bf16_2cta: aux required");
+  LV_REQUIRE(!(flags & LV_EPI_SCALE) || epi->scale_ptr, "lv_gemm_bf16_2cta: scale_ptr required");
+  if (k_splits < 1) k_splits = 1;
+  LV_REQUIRE(k_splits == 1 || (flags & LV_EPI_ATOMIC), "lv_gemm_bf16_2cta: k_splits > 1 requires LV_EPI_ATOMIC");
+
+  CUtensorMap tmA, tmB;
+  int rc;
+  if (a_mn) rc = make_tmap_2d_bf16(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 64, BK);
+  else      rc = make_tmap_2d_bf16(&tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, BK, BM_CTA);
+  if (rc) return rc;
+  if (b_mn) rc = make_tmap_2d_bf16(&tmB, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 64, BK);
+  else      rc = make_tmap_2d_bf16(&tmB, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, BK, BN_CTA);
+  if (rc) return rc;
+
+  gemm::Args g;
+  g.M = (int)M; g.N = (int)N; g.K = (int)K;
+  g.num_m_blks = (int)((M + 255) / 256);
+  g.num_n_blks = (int)((N + BN - 1) / BN);
+  g.num_kb = (int)((K + BK - 1) / BK);
+  if (k_splits > g.num_kb) k_splits = g.num_kb;
+  g.kb_per_split = (g.num_kb + k_splits - 1) / k_splits;
+  g.k_splits = (g.num_kb + g.kb_per_split - 1) / g.kb_per_split;
+  g.flags = flags | ((flags & LV_EPI_ATOMIC) ? LV_EPI_OUT_F32 : 0);
+  g.out = epi->out; g.ldo = epi->ldo;
+  g.out2 = epi->out2; g.ldo2 = epi->ldo2;
+  g.bias = epi->bias;
+  g.resid = epi->resid; g.ldr = epi->ldr;
+  g.aux = reinterpret_cast<const __nv_bfloat16*>(epi->aux); g.ldaux = epi->ldaux;
+  g.scale_ptr = epi->scale_ptr;
+
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (!a_mn && !b_mn) return dispatch<0, 0>(tmA, tmB, g, st);
+  if (!a_mn && b_mn) return dispatch<0, 1>(tmA, tmB, g, st);
+  if (a_mn && b_mn) return dispatch<1, 1>(tmA, tmB, g, st);
+  return dispatch<1, 0>(tmA, tmB, g, st);
+}

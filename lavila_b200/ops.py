@@ -43,15 +43,20 @@ def gemm(A, B, M, N, K, out, *, a_mn=0, b_mn=0, flags=0, out2=None, bias=None, r
         e.aux, e.ldaux = aux.data_ptr(), aux.stride(0)
     if scale is not None:
         e.scale_ptr = scale.data_ptr()
-    rc = L.lib().lv_gemm_bf16(A.data_ptr(), lda if lda is not None else A.stride(0), a_mn, B.data_ptr(),
-                              ldb if ldb is not None else B.stride(0), b_mn, M, N, K, k_splits, ctypes.byref(e),
-                              _stream())
+    fn = L.lib().lv_gemm_bf16_2cta if (USE_2CTA_GEMM and M >= 256) else L.lib().lv_gemm_bf16
+    rc = fn(A.data_ptr(), lda if lda is not None else A.stride(0), a_mn, B.data_ptr(),
+            ldb if ldb is not None else B.stride(0), b_mn, M, N, K, k_splits, ctypes.byref(e), _stream())
     L.check(rc, "lv_gemm_bf16")
     return out
 
 
+USE_2CTA_GEMM = False   # 256x256 CTA-pair tiles (lv_gemm_bf16_2cta)
+
+
 def wgrad_splits(m_out, n_in, k_tokens, sms=148):
-    tiles = ((m_out + 127) // 128) * ((n_in + 255) // 256)
+    bm = 256 if USE_2CTA_GEMM and m_out >= 256 else 128
+    sms = sms // 2 if bm == 256 else sms
+    tiles = ((m_out + bm - 1) // bm) * ((n_in + 255) // 256)
     kb = (k_tokens + 63) // 64
     return max(1, min(kb, (4 * sms + tiles - 1) // tiles))
 

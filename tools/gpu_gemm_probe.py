@@ -13,6 +13,10 @@ sys.path.insert(0, ".")
 from lavila_b200 import _lib as L  # noqa: E402
 
 
+import os
+TWO_CTA = os.environ.get("LV_2CTA", "0") == "1"
+
+
 def gemm(A, a_mn, B, b_mn, M, N, K, flags=0, out=None, out2=None, bias=None, resid=None, aux=None, scale=None,
          k_splits=1):
     e = L.LvGemmEpilogue()
@@ -29,8 +33,8 @@ def gemm(A, a_mn, B, b_mn, M, N, K, flags=0, out=None, out2=None, bias=None, res
     if scale is not None:
         e.scale_ptr = scale.data_ptr()
     st = torch.cuda.current_stream().cuda_stream
-    rc = L.lib().lv_gemm_bf16(A.data_ptr(), A.stride(0), a_mn, B.data_ptr(), B.stride(0), b_mn, M, N, K, k_splits,
-                              ctypes.byref(e), st)
+    fn = L.lib().lv_gemm_bf16_2cta if TWO_CTA else L.lib().lv_gemm_bf16
+    rc = fn(A.data_ptr(), A.stride(0), a_mn, B.data_ptr(), B.stride(0), b_mn, M, N, K, k_splits, ctypes.byref(e), st)
     L.check(rc, "lv_gemm_bf16")
 
 
