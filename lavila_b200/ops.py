@@ -50,7 +50,7 @@ def gemm(A, B, M, N, K, out, *, a_mn=0, b_mn=0, flags=0, out2=None, bias=None, r
     return out
 
 
-USE_2CTA_GEMM = False   # 256x256 CTA-pair tiles (lv_gemm_bf16_2cta)
+USE_2CTA_GEMM = True    # 256x256 CTA-pair tiles (lv_gemm_bf16_2cta) whenever M >= 256
 
 
 def wgrad_splits(m_out, n_in, k_tokens, sms=148):
