@@ -20,7 +20,7 @@ def test_library_builds_loads_and_exports_every_declared_symbol():
     lib = _lib.lib()
     assert lib.lv_version() == 1
     names = _declared()
-    assert len(names) >= 30, names
+    assert len(names) >= 25, names
     missing = [n for n in names if not hasattr(lib, n)]
     assert not missing, missing
     assert lib.lv_launch_count() == 0
