@@ -334,6 +334,9 @@ static_assert(FWD_SMEM <= 227 * 1024, "space attention forward: shared memory bu
 //        dQ_qt += dS K_kt                                (A operand = the same dS^T tile read MN-major)
 // dV/dK are complete after the two query tiles of a key tile, dQ after both key tiles.
 // TMEM columns: S^T 128 | dP^T 128 | dV 64 | dK 64 | dQ0 64 | dQ1 64 = 512.
+__device__ long long* g_dbg = nullptr;   // optional cycle-stamp buffer (lv_debug_set_buffer), CTA 0 only
+#define LV_STAMP(slot) do { if (g_dbg && blockIdx.x == 0 && it < 4) g_dbg[it * 64 + (slot)] = clock64(); } while (0)
+
 constexpr int B_ROWS = 256;
 constexpr int B_TILE_BYTES = B_ROWS * 128;    // Q, K, V, dO tiles (rows beyond n / n+1 stay zero)
 constexpr int B_STAGE_BYTES = 2 * 128 * 128;  // P^T / dS^T: 128 key rows x 128 query columns (2 atoms of 64)
@@ -483,7 +486,9 @@ space_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __gri
       constexpr uint32_t idesc_dq = make_idesc_bf16(128, HD, 1, 1);   // A MN-major (dS^T read transposed), B MN-major
       int it = 0;
       for (long long g = blockIdx.x; g < p.num_groups; g += gridDim.x, ++it) {
+        LV_STAMP(0);
         mbar_wait(bar_load, it & 1);
+        LV_STAMP(1);
         tc_fence_after();
 #pragma unroll 1
         for (int step = 0; step < 4; ++step) {
@@ -501,8 +506,10 @@ space_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __gri
                         make_smem_desc_sw128(do_base + qt * 16384 + ks * 32, 16, 1024), idesc_a, ks > 0);
           }
           tc_commit(bar_sdp);
+          LV_STAMP(2 + step * 4);
           // (B) needs the staged P^T / dS^T
           mbar_wait(bar_pds, step & 1);
+          LV_STAMP(3 + step * 4);
           tc_fence_after();
           const int nq_steps = qt ? 5 : 8;       // 80 or 128 query columns
           for (int s2 = 0; s2 < nq_steps; ++s2) {
@@ -519,6 +526,7 @@ space_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __gri
                         make_smem_desc_sw128(k_base + (kt * 128 + s2 * 16) * 128, 8192, 1024), idesc_dq, (kt > 0 || s2 > 0));
           }
           tc_commit(bar_mma3);
+          LV_STAMP(4 + step * 4);
         }
         tc_commit(bar_free);
       }
@@ -549,11 +557,14 @@ space_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __gri
         s_delta[et] = dl;
       }
       bar_sync_epi();
+      if (warp == 2 && lane == 0) LV_STAMP(20);
 #pragma unroll 1
       for (int step = 0; step < 4; ++step) {
         const int kt = step >> 1, qt = step & 1;
         mbar_wait(bar_sdp, step & 1);
+        if (warp == 2 && lane == 0) LV_STAMP(21 + step * 4);
         if (step > 0) mbar_wait(bar_mma3, (step - 1) & 1);   // previous (B) MMAs have consumed the staged tiles
+        if (warp == 2 && lane == 0) LV_STAMP(22 + step * 4);
         tc_fence_after();
         if (step == 2) {
           // ---- epilogue of key tile 0: dV (hf 0) / dK (hf 1)
@@ -609,13 +620,16 @@ space_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __gri
             }
           }
         }
+        if (warp == 2 && lane == 0) LV_STAMP(23 + step * 4);
         fence_proxy_async_smem();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_pds);
+        if (warp == 2 && lane == 0) LV_STAMP(24 + step * 4);
       }
       // ---- final epilogues: key tile 1 (dV / dK) and dQ0 / dQ1
       mbar_wait(bar_mma3, 1);
+      if (warp == 2 && lane == 0) LV_STAMP(40);
       tc_fence_after();
       {
         uint32_t a[32], b[32];
@@ -642,6 +656,7 @@ space_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __gri
         const int qrow = hf * 128 + row;
         if (qrow < Lq) store_row64(p.dqkv + (c.base_row + qrow) * p.ld_dqkv + c.h * HD, a, b, false);
       }
+      if (warp == 2 && lane == 0) LV_STAMP(41);
       tc_fence_before();
       bar_sync_epi();   // s_lse / s_delta of this group are dead; TMEM accumulators drained
     }
@@ -722,4 +737,10 @@ extern "C" int lv_space_attn_bwd_tc(const void* qkv, int64_t ld_qkv, const void*
   const long long grid = p.num_groups < sm_count() ? p.num_groups : sm_count();
   attn_tc::space_attn_bwd_tc_kernel<<<(unsigned)grid, attn_tc::NTHREADS, attn_tc::BWD_SMEM, (cudaStream_t)stream>>>(tm_qkv, tm_do, p);
   return check_launch("lv_space_attn_bwd_tc");
+}
+
+extern "C" int lv_debug_set_buffer(void* buf) {
+  long long* p = (long long*)buf;
+  cudaError_t e = cudaMemcpyToSymbol(lv::attn_tc::g_dbg, &p, sizeof(p));
+  return e == cudaSuccess ? 0 : lv::set_error((int)e, "lv_debug_set_buffer: %s", cudaGetErrorString(e));
 }
