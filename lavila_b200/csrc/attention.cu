@@ -98,15 +98,19 @@ struct GroupCoord {
   long long base_row;  // first group row (global row index)
   long long cls_row;
 };
-__device__ __forceinline__ GroupCoord decode_group(const Params& p, long long group) {
-  GroupCoord c;
-  const int in = (int)(group % p.inner);
-  const long long bh = group / p.inner;
-  c.h = (int)(bh % p.H);
-  c.b = (int)(bh / p.H);
+// CTA -> groups.  A CTA owns `groups_per_cta` consecutive inner positions of ONE (clip, head); CTAs are ordered
+// head-fastest, so CTAs that run at the same time read different heads of the same token rows (contiguous DRAM runs),
+// while the groups inside a CTA share (clip, head) and their CLS-key gradients can be reduced in shared memory.
+__device__ __forceinline__ bool decode_group(const Params& p, long long cta, int g_local, GroupCoord& c) {
+  const int jb_count = (p.inner + p.groups_per_cta - 1) / p.groups_per_cta;
+  c.h = (int)(cta % p.H);
+  const long long t = cta / p.H;
+  const int jb = (int)(t % jb_count);
+  c.b = (int)(t / jb_count);
+  const int in = jb * p.groups_per_cta + g_local;
   c.cls_row = (long long)c.b * p.clip_rows;
   c.base_row = c.cls_row + p.first + (long long)in * p.inner_stride;
-  return c;
+  return in < p.inner;
 }
 
 // Cooperative load of `rows_pad` rows x 64 bf16 into a swizzled tile.  Row r < n_rows comes from
@@ -130,12 +134,11 @@ group_attn_fwd_kernel(const Params p) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g_local = warp / p.wg, w_in_g = warp - g_local * p.wg;
-  const long long group = (long long)blockIdx.x * p.groups_per_cta + g_local;
-  const bool active = group < p.num_groups;
   const int q_rows = p.qt * 16, k_rows = NT * 8;
   const uint32_t gs = smem_u32(smem) + g_local * (q_rows + 2 * k_rows) * ROW_BYTES;
   const uint32_t sQ = gs, sK = gs + q_rows * ROW_BYTES, sV = sK + k_rows * ROW_BYTES;
-  const GroupCoord gc = decode_group(p, active ? group : 0);
+  GroupCoord gc;
+  const bool active = decode_group(p, blockIdx.x, g_local, gc);
   const int Lk = p.Lq + (p.has_cls ? 1 : 0);
   {
     const int tid = w_in_g * 32 + lane, nthr = p.wg * 32;
@@ -312,8 +315,6 @@ group_attn_bwd_kernel(const Params p, const int k_rows) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g_local = warp / p.wg, w_in_g = warp - g_local * p.wg;
-  const long long group = (long long)blockIdx.x * p.groups_per_cta + g_local;
-  const bool active = group < p.num_groups;
   const int q_rows = p.qt * 16;
   const int ds_pitch = (q_rows + 8) * 2;  // bytes
   const uint32_t gs = smem_u32(smem) + g_local * p.group_bytes;
@@ -327,7 +328,8 @@ group_attn_bwd_kernel(const Params p, const int k_rows) {
   float* cls_red = reinterpret_cast<float*>(smem + p.groups_per_cta * p.group_bytes) + g_local * 2 * HD;
   float* lse_s = reinterpret_cast<float*>(smem + (sLse - smem_u32(smem)));
   float* delta_s = reinterpret_cast<float*>(smem + (sDelta - smem_u32(smem)));
-  const GroupCoord gc = decode_group(p, active ? group : 0);
+  GroupCoord gc;
+  const bool active = decode_group(p, blockIdx.x, g_local, gc);
   const int Lk = p.Lq + (p.has_cls ? 1 : 0);
   const int tid = w_in_g * 32 + lane, nthr = p.wg * 32;
   {
@@ -523,21 +525,15 @@ group_attn_bwd_kernel(const Params p, const int k_rows) {
   if (p.has_cls && p.dcls_kv) {
     __syncthreads();
     const float* red_all = reinterpret_cast<const float*>(smem + p.groups_per_cta * p.group_bytes);
+    const int jb_count = (p.inner + p.groups_per_cta - 1) / p.groups_per_cta;
+    const int jb = (int)((blockIdx.x / p.H) % jb_count);
+    int n_active = p.inner - jb * p.groups_per_cta;
+    if (n_active > p.groups_per_cta) n_active = p.groups_per_cta;
+    const long long bh = (long long)(blockIdx.x / ((long long)p.H * jb_count)) * p.H + (blockIdx.x % p.H);
     for (int e = threadIdx.x; e < 2 * HD; e += blockDim.x) {
       float run = 0.f;
-      long long run_bh = -1;
-      for (int gl = 0; gl < p.groups_per_cta; ++gl) {
-        const long long gi = (long long)blockIdx.x * p.groups_per_cta + gl;
-        if (gi >= p.num_groups) break;
-        const long long bh = gi / p.inner;
-        if (bh != run_bh) {
-          if (run_bh >= 0) atomicAdd(p.dcls_kv + run_bh * 2 * HD + e, run);
-          run = 0.f;
-          run_bh = bh;
-        }
-        run += red_all[gl * 2 * HD + e];
-      }
-      if (run_bh >= 0) atomicAdd(p.dcls_kv + run_bh * 2 * HD + e, run);
+      for (int gl = 0; gl < n_active; ++gl) run += red_all[gl * 2 * HD + e];
+      atomicAdd(p.dcls_kv + bh * 2 * HD + e, run);
     }
   }
 }
@@ -726,7 +722,7 @@ int launch_fwd(attn::Params& p, cudaStream_t st) {
     configured = 227 * 1024;
   }
   LV_REQUIRE(smem <= 227 * 1024, "attention fwd: group does not fit in shared memory (%d bytes)", smem);
-  const long long grid = (p.num_groups + gpc - 1) / gpc;
+  const long long grid = (long long)(p.num_groups / p.inner) * ((p.inner + gpc - 1) / gpc);   // B*H CTAs per inner block
   attn::group_attn_fwd_kernel<NT><<<(unsigned)grid, gpc * wg * 32, smem, st>>>(p);
   return check_launch("lv_group_attn_fwd");
 }
@@ -789,7 +785,7 @@ extern "C" int lv_group_attn_bwd(const void* qkv, int64_t ld_qkv, const void* ou
     if (e != cudaSuccess) return set_error((int)e, "attention bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     configured = true;
   }
-  const long long grid = (p.num_groups + gpc - 1) / gpc;
+  const long long grid = (long long)(p.num_groups / p.inner) * ((p.inner + gpc - 1) / gpc);
   attn::group_attn_bwd_kernel<<<(unsigned)grid, gpc * wg * 32, smem, (cudaStream_t)stream>>>(p, k_rows);
   return check_launch("lv_group_attn_bwd");
 }
