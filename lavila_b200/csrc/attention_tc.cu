@@ -61,13 +61,11 @@ struct Coord {
 };
 template <class P>
 __device__ __forceinline__ Coord decode(const P& p, long long g) {
-  // head-fastest order: CTAs that run at the same time work on different heads of the SAME token rows, so their
-  // 128-byte row pieces together form contiguous 64*H*2-byte runs in DRAM (measured: TMA wait 15K -> cycles per group)
-  Coord c;
-  c.h = (int)(g % p.H);
-  const long long bf = g / p.H;
-  c.f = (int)(bf % p.T);
-  c.b = (int)(bf / p.T);
+  Coord c;   // frame-fastest (head-fastest order was measured: no gain for the TMA gathers, slower read-modify-write)
+  c.f = (int)(g % p.T);
+  const long long bh = g / p.T;
+  c.h = (int)(bh % p.H);
+  c.b = (int)(bh / p.H);
   c.cls_row = (long long)c.b * p.clip_rows;
   c.base_row = c.cls_row + 1 + (long long)c.f * p.n;
   return c;
