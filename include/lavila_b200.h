@@ -137,6 +137,11 @@ int lv_cls_attn_fwd(const void* qkv, int64_t ld_qkv, void* out, int64_t ld_out, 
 int lv_cls_attn_bwd(const void* qkv, int64_t ld_qkv, const void* out, int64_t ld_out, const void* dout, int64_t ld_dout,
                     const float* lse, void* dqkv, int64_t ld_dqkv, float* dcls_kv, int B, int H, int N, void* stream);
 int lv_cls_kv_finalize(const float* dcls_kv, void* dqkv, int64_t ld_dqkv, int B, int H, int N, void* stream);
+/* CLS query attention with separate operands: q bf16 [B, D], kv bf16 [B*N, 2D] = [k | v], out bf16 [B, D], lse [B, H].
+ * Used by the last SpaceTimeBlock, of which only the CLS row is consumed (timesformer.py:376-378). */
+int lv_cls_query_attn_fwd(const void* q, const void* kv, void* out, float* lse, int B, int H, int N, void* stream);
+int lv_cls_query_attn_bwd(const void* q, const void* kv, const void* out, const void* dout, const float* lse, void* dq,
+                          void* dkv, int B, int H, int N, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * HBM-bound glue (elementwise.cu)
@@ -165,6 +170,8 @@ int lv_argmax_i64(const int64_t* text, int32_t* out, int B, int L, void* stream)
 /* scatter=0: dst[r] = src[r*rows_per + idx[r]];  scatter=1: dst[r*rows_per + idx[r]] = src[r].  fp32 rows of W. */
 int lv_gather_rows_f32(const float* src, const int32_t* idx, float* dst, int R, int rows_per, int W, int scatter,
                        void* stream);
+/* dst[r*stride + c] += src[r*W + c] for R strided rows (dst bf16 or fp32). */
+int lv_add_rows(void* dst, int dst_is_bf16, int64_t stride, const float* src, int R, int W, void* stream);
 /* F.normalize(dim=-1) (models.py:169-170) and its gradient. */
 int lv_l2norm_fwd(const float* x, float* y, float* norm, int R, int E, void* stream);
 int lv_l2norm_bwd(const float* dy, const float* y, const float* norm, float* dx, int R, int E, void* stream);

@@ -15,6 +15,9 @@ SIGNATURES = {
     "lv_cls_attn_fwd": [P, L, P, L, P, I, I, I, P],
     "lv_cls_attn_bwd": [P, L, P, L, P, L, P, P, L, P, I, I, I, P],
     "lv_cls_kv_finalize": [P, P, L, I, I, I, P],
+    "lv_cls_query_attn_fwd": [P, P, P, P, I, I, I, P],
+    "lv_cls_query_attn_bwd": [P, P, P, P, P, P, P, I, I, I, P],
+    "lv_add_rows": [P, I, L, P, I, I, P],
     "lv_cast_f32_bf16": [P, P, L, P],
     "lv_colsum_bf16": [P, L, L, I, P, P],
     "lv_patch_im2col": [P, P, I, I, I, I, I, I, L, P],

@@ -556,24 +556,40 @@ __device__ __forceinline__ float oct_sum(float v) {  // sum over the 8 lanes tha
   return v + __shfl_xor_sync(0xffffffffu, v, 4);
 }
 
+// Addressing (elements): query of clip b at q + b*q_bs; key/value j of clip b at k|v + (b*N + j)*ld_kv;
+// output at out + b*o_bs; lse at lse + b*l_bs  (+ h*64 / + h for the head).
+struct ClsAddr {
+  const __nv_bfloat16 *q, *k, *v;
+  long long q_bs, ld_kv;
+  __nv_bfloat16* out;
+  long long o_bs;
+  float* lse;
+  long long l_bs;
+  // backward
+  const __nv_bfloat16* dout;
+  long long do_bs;
+  __nv_bfloat16 *dq, *dk, *dv;
+  long long dq_bs, ld_dkv;
+  float* dcls_kv;       // when non-null the CLS key/value row (j = 0) goes here in fp32 instead of dk/dv row 0
+};
+
 __global__ void __launch_bounds__(CLS_THREADS)
-cls_attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld, __nv_bfloat16* __restrict__ out, long long ldo,
-                    float* __restrict__ lse, int H, int D, int N, float scale) {
+cls_attn_fwd_kernel(const ClsAddr a, int H, int N, float scale) {
   __shared__ float s_m[CLS_GROUPS], s_l[CLS_GROUPS], s_acc[CLS_GROUPS][HD];
   const int b = blockIdx.x / H, h = blockIdx.x - b * H;
   const long long row0 = (long long)b * N;
   const int tid = threadIdx.x, grp = tid >> 3, c = tid & 7;
   float q[8];
-  unpack8(__ldg(reinterpret_cast<const uint4*>(qkv + row0 * ld + h * HD + c * 8)), q);
+  unpack8(__ldg(reinterpret_cast<const uint4*>(a.q + b * a.q_bs + h * HD + c * 8)), q);
   float m = -INFINITY, l = 0.f, acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   const int iters = (N + CLS_GROUPS - 1) / CLS_GROUPS;
   for (int it = 0; it < iters; ++it) {
     const int j = it * CLS_GROUPS + grp;
     const bool ok = j < N;
-    const __nv_bfloat16* base = qkv + (row0 + (ok ? j : 0)) * ld + h * HD + c * 8;
+    const long long roff = (row0 + (ok ? j : 0)) * a.ld_kv + h * HD + c * 8;
     float k[8], v[8];
-    unpack8(__ldg(reinterpret_cast<const uint4*>(base + D)), k);
-    unpack8(__ldg(reinterpret_cast<const uint4*>(base + 2 * D)), v);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(a.k + roff)), k);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(a.v + roff)), v);
     float sp = 0.f;
 #pragma unroll
     for (int e = 0; e < 8; ++e) sp += q[e] * k[e];
@@ -600,40 +616,37 @@ cls_attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld, __nv_bf
       Lsum += s_l[g2] * w;
       o += s_acc[g2][tid] * w;
     }
-    out[row0 * ldo + h * HD + tid] = __float2bfloat16_rn(o / Lsum);
-    if (tid == 0) lse[row0 * H + h] = M + logf(Lsum);
+    a.out[b * a.o_bs + h * HD + tid] = __float2bfloat16_rn(o / Lsum);
+    if (tid == 0) a.lse[b * a.l_bs + h] = M + logf(Lsum);
   }
 }
 
 // Backward of the CLS query attention.  Writes: dqkv[cls row, q part]; dqkv[rows 1..N-1, k and v parts] (this query's
 // contribution; the group backward adds its own on top); dcls_kv[b,h] (fp32) = contribution to the CLS key/value.
 __global__ void __launch_bounds__(CLS_THREADS)
-cls_attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld, const __nv_bfloat16* __restrict__ out,
-                    long long ldo, const __nv_bfloat16* __restrict__ dout, long long lddo,
-                    const float* __restrict__ lse, __nv_bfloat16* __restrict__ dqkv, long long lddq,
-                    float* __restrict__ dcls_kv, int H, int D, int N, float scale) {
+cls_attn_bwd_kernel(const ClsAddr a, int H, int N, float scale) {
   __shared__ float s_dq[CLS_GROUPS][HD];
   const int b = blockIdx.x / H, h = blockIdx.x - b * H;
   const long long row0 = (long long)b * N;
   const int tid = threadIdx.x, grp = tid >> 3, c = tid & 7;
   float q[8], dO[8], o[8];
-  unpack8(__ldg(reinterpret_cast<const uint4*>(qkv + row0 * ld + h * HD + c * 8)), q);
-  unpack8(__ldg(reinterpret_cast<const uint4*>(dout + row0 * lddo + h * HD + c * 8)), dO);
-  unpack8(__ldg(reinterpret_cast<const uint4*>(out + row0 * ldo + h * HD + c * 8)), o);
+  unpack8(__ldg(reinterpret_cast<const uint4*>(a.q + b * a.q_bs + h * HD + c * 8)), q);
+  unpack8(__ldg(reinterpret_cast<const uint4*>(a.dout + b * a.do_bs + h * HD + c * 8)), dO);
+  unpack8(__ldg(reinterpret_cast<const uint4*>(a.out + b * a.o_bs + h * HD + c * 8)), o);
   float dpart = 0.f;
 #pragma unroll
   for (int e = 0; e < 8; ++e) dpart += dO[e] * o[e];
   const float delta = oct_sum(dpart);
-  const float L = lse[row0 * H + h];
+  const float L = a.lse[b * a.l_bs + h];
   float dq[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   const int iters = (N + CLS_GROUPS - 1) / CLS_GROUPS;
   for (int it = 0; it < iters; ++it) {
     const int j = it * CLS_GROUPS + grp;
     const bool ok = j < N;
-    const __nv_bfloat16* base = qkv + (row0 + (ok ? j : 0)) * ld + h * HD + c * 8;
+    const long long roff = (row0 + (ok ? j : 0)) * a.ld_kv + h * HD + c * 8;
     float k[8], v[8];
-    unpack8(__ldg(reinterpret_cast<const uint4*>(base + D)), k);
-    unpack8(__ldg(reinterpret_cast<const uint4*>(base + 2 * D)), v);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(a.k + roff)), k);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(a.v + roff)), v);
     float sp = 0.f, dpp = 0.f;
 #pragma unroll
     for (int e = 0; e < 8; ++e) { sp += q[e] * k[e]; dpp += dO[e] * v[e]; }
@@ -649,16 +662,16 @@ cls_attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld, const _
         dk[e] = dsj * q[e];
         dv[e] = pj * dO[e];
       }
-      if (j == 0) {
-        float* kb = dcls_kv + ((long long)b * H + h) * 2 * HD + c * 8;
+      if (j == 0 && a.dcls_kv) {
+        float* kb = a.dcls_kv + ((long long)b * H + h) * 2 * HD + c * 8;
 #pragma unroll
         for (int e = 0; e < 8; ++e) { kb[e] = dk[e]; kb[HD + e] = dv[e]; }
       } else {
-        __nv_bfloat16* dst = dqkv + (row0 + j) * lddq + h * HD + c * 8;
-        *reinterpret_cast<uint4*>(dst + D) = make_uint4(pack_bf16x2(dk[0], dk[1]), pack_bf16x2(dk[2], dk[3]),
-                                                         pack_bf16x2(dk[4], dk[5]), pack_bf16x2(dk[6], dk[7]));
-        *reinterpret_cast<uint4*>(dst + 2 * D) = make_uint4(pack_bf16x2(dv[0], dv[1]), pack_bf16x2(dv[2], dv[3]),
-                                                             pack_bf16x2(dv[4], dv[5]), pack_bf16x2(dv[6], dv[7]));
+        const long long doff = (row0 + j) * a.ld_dkv + h * HD + c * 8;
+        *reinterpret_cast<uint4*>(a.dk + doff) = make_uint4(pack_bf16x2(dk[0], dk[1]), pack_bf16x2(dk[2], dk[3]),
+                                                            pack_bf16x2(dk[4], dk[5]), pack_bf16x2(dk[6], dk[7]));
+        *reinterpret_cast<uint4*>(a.dv + doff) = make_uint4(pack_bf16x2(dv[0], dv[1]), pack_bf16x2(dv[2], dv[3]),
+                                                            pack_bf16x2(dv[4], dv[5]), pack_bf16x2(dv[6], dv[7]));
       }
     }
   }
@@ -668,7 +681,7 @@ cls_attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld, const _
   if (tid < HD) {
     float t = 0.f;
     for (int g2 = 0; g2 < CLS_GROUPS; ++g2) t += s_dq[g2][tid];
-    dqkv[row0 * lddq + h * HD + tid] = __float2bfloat16_rn(t);
+    a.dq[b * a.dq_bs + h * HD + tid] = __float2bfloat16_rn(t);
   }
 }
 
@@ -794,8 +807,12 @@ extern "C" int lv_cls_attn_fwd(const void* qkv, int64_t ld_qkv, void* out, int64
                                void* stream) {
   LV_REQUIRE(qkv && out && lse && B > 0 && H > 0 && N > 0, "lv_cls_attn_fwd: bad arguments");
   LV_REQUIRE(ld_qkv % 8 == 0, "lv_cls_attn_fwd: ld_qkv must be a multiple of 8");
-  attn::cls_attn_fwd_kernel<<<B * H, attn::CLS_THREADS, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)qkv, ld_qkv, (__nv_bfloat16*)out, ld_out, lse, H, H * attn::HD, N, 0.125f);
+  attn::ClsAddr a{};
+  const __nv_bfloat16* base = (const __nv_bfloat16*)qkv;
+  const long long D = (long long)H * attn::HD;
+  a.q = base; a.k = base + D; a.v = base + 2 * D; a.q_bs = (long long)N * ld_qkv; a.ld_kv = ld_qkv;
+  a.out = (__nv_bfloat16*)out; a.o_bs = (long long)N * ld_out; a.lse = lse; a.l_bs = (long long)N * H;
+  attn::cls_attn_fwd_kernel<<<B * H, attn::CLS_THREADS, 0, (cudaStream_t)stream>>>(a, H, N, 0.125f);
   return check_launch("lv_cls_attn_fwd");
 }
 
@@ -804,9 +821,16 @@ extern "C" int lv_cls_attn_bwd(const void* qkv, int64_t ld_qkv, const void* out,
                                int N, void* stream) {
   LV_REQUIRE(qkv && out && dout && lse && dqkv && dcls_kv && B > 0 && H > 0 && N > 0, "lv_cls_attn_bwd: bad arguments");
   LV_REQUIRE(ld_qkv % 8 == 0 && ld_dqkv % 8 == 0, "lv_cls_attn_bwd: leading dimensions must be multiples of 8");
-  attn::cls_attn_bwd_kernel<<<B * H, attn::CLS_THREADS, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)qkv, ld_qkv, (const __nv_bfloat16*)out, ld_out, (const __nv_bfloat16*)dout, ld_dout, lse,
-      (__nv_bfloat16*)dqkv, ld_dqkv, dcls_kv, H, H * attn::HD, N, 0.125f);
+  attn::ClsAddr a{};
+  const __nv_bfloat16* base = (const __nv_bfloat16*)qkv;
+  __nv_bfloat16* dbase = (__nv_bfloat16*)dqkv;
+  const long long D = (long long)H * attn::HD;
+  a.q = base; a.k = base + D; a.v = base + 2 * D; a.q_bs = (long long)N * ld_qkv; a.ld_kv = ld_qkv;
+  a.out = (__nv_bfloat16*)out; a.o_bs = (long long)N * ld_out; a.lse = (float*)lse; a.l_bs = (long long)N * H;
+  a.dout = (const __nv_bfloat16*)dout; a.do_bs = (long long)N * ld_dout;
+  a.dq = dbase; a.dq_bs = (long long)N * ld_dqkv; a.dk = dbase + D; a.dv = dbase + 2 * D; a.ld_dkv = ld_dqkv;
+  a.dcls_kv = dcls_kv;
+  attn::cls_attn_bwd_kernel<<<B * H, attn::CLS_THREADS, 0, (cudaStream_t)stream>>>(a, H, N, 0.125f);
   return check_launch("lv_cls_attn_bwd");
 }
 
@@ -814,4 +838,33 @@ extern "C" int lv_cls_kv_finalize(const float* dcls_kv, void* dqkv, int64_t ld_d
   LV_REQUIRE(dcls_kv && dqkv && B > 0 && H > 0, "lv_cls_kv_finalize: bad arguments");
   attn::cls_kv_finalize_kernel<<<B * H, 128, 0, (cudaStream_t)stream>>>(dcls_kv, (__nv_bfloat16*)dqkv, ld_dqkv, H, H * attn::HD, N);
   return check_launch("lv_cls_kv_finalize");
+}
+
+// CLS query attention with separate q [B, D], packed kv [B*N, 2D] = [k | v] (the last block's CLS-only tail: only the
+// CLS row of the final SpaceTimeBlock is consumed by norm(x)[:, 0], lavila/models/timesformer.py:376-378).
+extern "C" int lv_cls_query_attn_fwd(const void* q, const void* kv, void* out, float* lse, int B, int H, int N, void* stream) {
+  LV_REQUIRE(q && kv && out && lse && B > 0 && H > 0 && N > 0, "lv_cls_query_attn_fwd: bad arguments");
+  attn::ClsAddr a{};
+  const long long D = (long long)H * attn::HD;
+  a.q = (const __nv_bfloat16*)q; a.q_bs = D;
+  a.k = (const __nv_bfloat16*)kv; a.v = a.k + D; a.ld_kv = 2 * D;
+  a.out = (__nv_bfloat16*)out; a.o_bs = D; a.lse = lse; a.l_bs = H;
+  attn::cls_attn_fwd_kernel<<<B * H, attn::CLS_THREADS, 0, (cudaStream_t)stream>>>(a, H, N, 0.125f);
+  return check_launch("lv_cls_query_attn_fwd");
+}
+
+extern "C" int lv_cls_query_attn_bwd(const void* q, const void* kv, const void* out, const void* dout, const float* lse,
+                                     void* dq, void* dkv, int B, int H, int N, void* stream) {
+  LV_REQUIRE(q && kv && out && dout && lse && dq && dkv && B > 0 && H > 0 && N > 0, "lv_cls_query_attn_bwd: bad arguments");
+  attn::ClsAddr a{};
+  const long long D = (long long)H * attn::HD;
+  a.q = (const __nv_bfloat16*)q; a.q_bs = D;
+  a.k = (const __nv_bfloat16*)kv; a.v = a.k + D; a.ld_kv = 2 * D;
+  a.out = (__nv_bfloat16*)out; a.o_bs = D; a.lse = (float*)lse; a.l_bs = H;
+  a.dout = (const __nv_bfloat16*)dout; a.do_bs = D;
+  a.dq = (__nv_bfloat16*)dq; a.dq_bs = D;
+  a.dk = (__nv_bfloat16*)dkv; a.dv = a.dk + D; a.ld_dkv = 2 * D;
+  a.dcls_kv = nullptr;
+  attn::cls_attn_bwd_kernel<<<B * H, attn::CLS_THREADS, 0, (cudaStream_t)stream>>>(a, H, N, 0.125f);
+  return check_launch("lv_cls_query_attn_bwd");
 }

@@ -263,10 +263,33 @@ __global__ void l2norm_bwd_kernel(const float* __restrict__ dy, const float* __r
     dx[(long long)r * E + c] = (dy[(long long)r * E + c] - y[(long long)r * E + c] * s) * inv;
 }
 
+// dst[r*stride + c] += src[r*W + c]  (dst bf16 or fp32; R rows picked with a row stride, e.g. the CLS row of every clip)
+template <bool BF16>
+__global__ void add_rows_kernel(void* __restrict__ dst, long long stride, const float* __restrict__ src, int R, int W) {
+  const int r = blockIdx.x;
+  for (int c = threadIdx.x; c < W; c += blockDim.x) {
+    const float v = src[(long long)r * W + c];
+    if (BF16) {
+      __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(dst) + (long long)r * stride + c;
+      *d = __float2bfloat16_rn(__bfloat162float(*d) + v);
+    } else {
+      float* d = reinterpret_cast<float*>(dst) + (long long)r * stride + c;
+      *d += v;
+    }
+  }
+}
+
 }  // namespace ew
 }  // namespace lv
 
 using namespace lv;
+
+extern "C" int lv_add_rows(void* dst, int dst_is_bf16, int64_t stride, const float* src, int R, int W, void* stream) {
+  LV_REQUIRE(dst && src && R > 0 && W > 0, "lv_add_rows: bad arguments");
+  if (dst_is_bf16) ew::add_rows_kernel<true><<<R, 256, 0, (cudaStream_t)stream>>>(dst, stride, src, R, W);
+  else ew::add_rows_kernel<false><<<R, 256, 0, (cudaStream_t)stream>>>(dst, stride, src, R, W);
+  return check_launch("lv_add_rows");
+}
 
 extern "C" int lv_cast_f32_bf16(const float* in, void* out, int64_t n, void* stream) {
   LV_REQUIRE(in && out && n >= 0, "lv_cast_f32_bf16: bad arguments");

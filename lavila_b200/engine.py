@@ -258,6 +258,99 @@ class SpaceTimeBlockFn(torch.autograd.Function):
         return (dx.view(B, N, D), None, None, None, None, dgate) + tuple(grads[k] for k in BLOCK_PARAM_ORDER)
 
 
+class LastBlockClsFn(torch.autograd.Function):
+    """The LAST SpaceTimeBlock when only its CLS row is consumed (`norm(x)[:, 0]`, timesformer.py:376-378).
+
+    Same arithmetic as SpaceTimeBlockFn for the rows that matter: the time sub-block runs in full (every token's
+    key/value of the space attention depends on it), but the space attention is evaluated for the CLS query only (it
+    attends to all N tokens, timesformer.py:119), and the output projection and the MLP run on B rows instead of B*N.
+    Skips 40/64 of the block's GEMM FLOPs, the whole space group attention and two LayerNorm passes, fwd and bwd.
+    x: fp32 [B, N, D] -> fp32 [B, D] (CLS rows of the block output)."""
+
+    @staticmethod
+    def forward(ctx, x, heads, frames, patches, eps, gate, *params):
+        ps = dict(zip(BLOCK_PARAM_ORDER, params))
+        B, N, D = x.shape
+        M = B * N
+        dev = x.device
+        x2 = x.contiguous().view(M, D)
+        if x2.dtype != F32:
+            x2 = x2.float()
+        dims = dict(B=B, H=heads, T=frames, n=patches, N=N, L=0)
+        xt, s_t = attn_sub_fwd(x2, x2, _attn_params(ps, "norm3", "timeattn"), dims, MODE_TIME, eps, gate=gate)
+        # ---- space attention, CLS query only
+        ln1 = torch.empty(M, D, device=dev, dtype=BF16)
+        ops.layernorm_fwd(xt, ps["norm1.weight"], ps["norm1.bias"], eps, M, D, y_bf16=ln1)
+        wqkv, bqkv = SHADOW.get(ps["attn.qkv.weight"]), ps["attn.qkv.bias"]
+        kv = torch.empty(M, 2 * D, device=dev, dtype=BF16)
+        ops.gemm(ln1, wqkv[D:], M, 2 * D, D, kv, flags=L.EPI_BIAS, bias=bqkv[D:])
+        q = torch.empty(B, D, device=dev, dtype=BF16)
+        ops.gemm(ln1, wqkv[:D], B, D, D, q, flags=L.EPI_BIAS, bias=bqkv[:D], lda=N * D)       # CLS rows: row stride N*D
+        att = torch.empty(B, D, device=dev, dtype=BF16)
+        lse = torch.empty(B, heads, device=dev, dtype=F32)
+        ops.cls_query_attn_fwd(q, kv, att, lse, B, heads, N)
+        r = torch.empty(B, D, device=dev, dtype=F32)                                              # r = x_cls + proj(att)
+        ops.gemm(att, SHADOW.get(ps["attn.proj.weight"]), B, D, D, r, flags=L.EPI_BIAS | L.EPI_RESID,
+                 bias=ps["attn.proj.bias"], resid=x2.view(B, N * D))       # residual = CLS rows of x (row stride N*D)
+        y, s_m = mlp_sub_fwd(r, _mlp_params(ps), eps)
+        ctx.saved = (s_t, s_m, ps, gate, xt, ln1, kv, q, att, lse)
+        ctx.shape = (B, N, D, heads, eps)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        s_t, s_m, ps, gate, xt, ln1, kv, q, att, lse = ctx.saved
+        ctx.saved = None
+        B, N, D, heads, eps = ctx.shape
+        M = B * N
+        dev = dy.device
+        _GRAD_BF16.clear()
+        dy = dy.contiguous().float()
+        dy_b = ops.cast_bf16(dy)
+        dr, dr_b, g_m = mlp_sub_bwd(dy, dy_b, _mlp_params(ps), s_m)            # [B, D]
+        # ---- proj (B rows)
+        g_pw, g_pb = _zeros_like_param(ps["attn.proj.weight"]), _zeros_like_param(ps["attn.proj.bias"])
+        _wgrad(dr_b, att, D, D, B, g_pw)
+        ops.colsum_bf16(dr_b, B, D, g_pb)
+        datt = torch.empty(B, D, device=dev, dtype=BF16)
+        ops.gemm(dr_b, SHADOW.get(ps["attn.proj.weight"]), B, D, D, datt, b_mn=1)
+        # ---- CLS attention backward: dq [B, D], dk/dv for every token [M, 2D]
+        dq = torch.empty(B, D, device=dev, dtype=BF16)
+        dkv = torch.empty(M, 2 * D, device=dev, dtype=BF16)
+        ops.cls_query_attn_bwd(q, kv, att, datt, lse, dq, dkv, B, heads, N)
+        # ---- qkv projection: k/v part over all rows, q part over the CLS rows
+        g_qw, g_qb = _zeros_like_param(ps["attn.qkv.weight"]), _zeros_like_param(ps["attn.qkv.bias"])
+        wqkv = SHADOW.get(ps["attn.qkv.weight"])
+        _wgrad(dkv, ln1, 2 * D, D, M, g_qw[D:])
+        ops.colsum_bf16(dkv, M, 2 * D, g_qb[D:])
+        ops.gemm(dq, ln1, D, D, B, g_qw[:D], a_mn=1, b_mn=1, flags=L.EPI_ATOMIC, ldb=N * D)       # dWq += dq^T ln1[cls rows]
+        ops.colsum_bf16(dq, B, D, g_qb[:D])
+        dln1 = torch.empty(M, D, device=dev, dtype=BF16)
+        ops.gemm(dkv, wqkv[D:], M, D, 2 * D, dln1, b_mn=1)
+        dln1_cls = torch.empty(B, D, device=dev, dtype=F32)
+        ops.gemm(dq, wqkv[:D], B, D, D, dln1_cls, b_mn=1)
+        ops.add_rows(dln1, N * D, dln1_cls, B, D)                                                  # CLS rows also feed q
+        del dkv
+        # ---- norm1 backward (all rows), then the time sub-block
+        g_n1w, g_n1b = _zeros_like_param(ps["norm1.weight"]), _zeros_like_param(ps["norm1.bias"])
+        dxt = torch.empty(M, D, device=dev, dtype=F32)
+        dxt_b = torch.empty(M, D, device=dev, dtype=BF16)
+        ops.layernorm_bwd(dln1, xt, ps["norm1.weight"], eps, M, D, dx=dxt, dx_bf16=dxt_b, dgamma=g_n1w, dbeta=g_n1b)
+        del dln1
+        dx, dx_b, g_t = attn_sub_bwd(dxt, dxt_b, _attn_params(ps, "norm3", "timeattn"), s_t, adds=(dxt,), want_bf16=False)
+        ops.add_rows(dx, N * D, dr, B, D)                       # space residual r = x_cls + ... reaches x at the CLS rows only
+        grads = {
+            "norm3.weight": g_t["ln_w"], "norm3.bias": g_t["ln_b"], "timeattn.qkv.weight": g_t["qkv_w"],
+            "timeattn.qkv.bias": g_t["qkv_b"], "timeattn.proj.weight": g_t["proj_w"], "timeattn.proj.bias": g_t["proj_b"],
+            "norm1.weight": g_n1w, "norm1.bias": g_n1b, "attn.qkv.weight": g_qw, "attn.qkv.bias": g_qb,
+            "attn.proj.weight": g_pw, "attn.proj.bias": g_pb,
+            "norm2.weight": g_m["ln_w"], "norm2.bias": g_m["ln_b"], "mlp.fc1.weight": g_m["fc1_w"],
+            "mlp.fc1.bias": g_m["fc1_b"], "mlp.fc2.weight": g_m["fc2_w"], "mlp.fc2.bias": g_m["fc2_b"],
+        }
+        dgate = g_t.get("gate") if gate is not None else None
+        return (dx.view(B, N, D), None, None, None, None, dgate) + tuple(grads[k] for k in BLOCK_PARAM_ORDER)
+
+
 # ----------------------------------------------------------------------------------------------- text block
 TEXT_PARAM_ORDER = (
     "ln_1.weight", "ln_1.bias", "attn.in_proj_weight", "attn.in_proj_bias", "attn.out_proj.weight", "attn.out_proj.bias",

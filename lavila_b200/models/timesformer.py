@@ -145,6 +145,12 @@ class SpaceTimeBlock(nn.Module):
                 self.norm2.weight, self.norm2.bias, self.mlp.fc1.weight, self.mlp.fc1.bias, self.mlp.fc2.weight,
                 self.mlp.fc2.bias)
 
+    def forward_cls_only(self, x, time_n, space_f):
+        """Last block of a `cls_at_last` forward: returns only the CLS rows [B, D] of the block output."""
+        gate = getattr(self, "alpha_timeattn", None)
+        return E.LastBlockClsFn.apply(x, self.num_heads, int(space_f), int(time_n), float(self.norm1.eps), gate,
+                                      *self._params())
+
     def forward(self, x, einops_from_space, einops_to_space, einops_from_time, einops_to_time, time_n, space_f,
                 use_checkpoint=False):
         # use_checkpoint is accepted for API parity; the fused block already saves only bf16 operands + fp32 residuals.
@@ -198,6 +204,7 @@ class SpaceTimeTransformer(nn.Module):
         nn.init.trunc_normal_(self.cls_token, std=.02)
         if num_frames == 1:
             self.apply(self._init_weights)
+        self.cls_only_tail = True   # see _features_bcthw
         self.einops_from_space = 'b (f n) d'
         self.einops_to_space = '(b f) n d'
         self.einops_from_time = 'b (f n) d'
@@ -248,7 +255,14 @@ class SpaceTimeTransformer(nn.Module):
         x = E.PatchEmbedStemFn.apply(x_bcthw, pe.weight, pe.bias, self.cls_token, self.pos_embed, self.temporal_embed,
                                      lw, lb, self.patch_embed.patch_size[0])
         n, f = self.patches_per_frame, T
-        for blk in self.blocks:
+        last = len(self.blocks) - 1
+        for i, blk in enumerate(self.blocks):
+            if cls_at_last and i == last and self.cls_only_tail:
+                # only norm(x)[:, 0] is consumed: the last block produces its CLS rows directly (same numbers, 40/64 of
+                # its GEMM work and the whole space group attention skipped)
+                x = blk.forward_cls_only(x, time_n=n, space_f=f)
+                x = E.LayerNormFn.apply(x, self.norm.weight, self.norm.bias, float(self.norm.eps))
+                return self.pre_logits(x)
             x = blk(x, self.einops_from_space, self.einops_to_space, self.einops_from_time, self.einops_to_time,
                     time_n=n, space_f=f, use_checkpoint=use_checkpoint)
         if cls_at_last:

@@ -128,6 +128,22 @@ def cls_attn_bwd(qkv, out, dout, lse, dqkv, dcls_kv, B, H, N):
     L.check(rc, "lv_cls_attn_bwd")
 
 
+def cls_query_attn_fwd(q, kv, out, lse, B, H, N):
+    rc = L.lib().lv_cls_query_attn_fwd(q.data_ptr(), kv.data_ptr(), out.data_ptr(), lse.data_ptr(), B, H, N, _stream())
+    L.check(rc, "lv_cls_query_attn_fwd")
+
+
+def cls_query_attn_bwd(q, kv, out, dout, lse, dq, dkv, B, H, N):
+    rc = L.lib().lv_cls_query_attn_bwd(q.data_ptr(), kv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(),
+                                       dq.data_ptr(), dkv.data_ptr(), B, H, N, _stream())
+    L.check(rc, "lv_cls_query_attn_bwd")
+
+
+def add_rows(dst, stride, src, R, W):
+    rc = L.lib().lv_add_rows(dst.data_ptr(), 1 if dst.dtype == BF16 else 0, stride, src.data_ptr(), R, W, _stream())
+    L.check(rc, "lv_add_rows")
+
+
 def cls_kv_finalize(dcls_kv, dqkv, B, H, N):
     rc = L.lib().lv_cls_kv_finalize(dcls_kv.data_ptr(), dqkv.data_ptr(), dqkv.stride(0), B, H, N, _stream())
     L.check(rc, "lv_cls_kv_finalize")

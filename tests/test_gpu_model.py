@@ -107,3 +107,24 @@ def test_state_dict_roundtrip():
     sd = m.state_dict()
     for k, v in params.items():
         assert torch.equal(sd[k].cpu(), v), k
+
+
+def test_cls_only_tail_equals_full_last_block():
+    """The last block's CLS-only shortcut must reproduce the full block (same kernels, fewer rows)."""
+    from lavila_b200.models.loss import CLIPLoss
+    cfg = dict(GOLD["norm"]["cfg"], depth=3)
+    params = O.init_params(cfg, seed=3, gated=True)
+    frames, text = O.synthetic_batch(cfg, 4, seed=9)
+    res = {}
+    for tail in (True, False):
+        model = build_clip(cfg, params, gated=True)
+        model.visual.cls_only_tail = tail
+        out = model(frames.to(DEV), text.to(DEV), norm_embed=True)
+        CLIPLoss()(out)["loss"].backward()
+        res[tail] = (out["image_embed"].detach().clone(), {n: p.grad.detach().clone() for n, p in model.named_parameters()})
+    assert rel_l2(res[True][0], res[False][0]) < 2e-3
+    for n, g in res[False][1].items():
+        if float(g.norm()) < 1e-9:
+            continue
+        r = rel_l2(res[True][1][n], g)
+        assert r < 3e-2, "%s: %.3e" % (n, r)
