@@ -281,8 +281,15 @@ def gemm_roofline(step_fn, ops, torch):
     tot_ms = sum(a.elapsed_time(b) for a, b, _ in rec)
     tot_fl = sum(f for _, _, f in rec)
     ach = tot_fl / (tot_ms / 1e3) / 1e12
-    return {"bound": "tensor", "kernel": "lv::gemm::gemm_bf16_kernel (tcgen05, all %d launches of one step)" % len(rec),
-            "achieved": round(ach, 1), "peak": peak, "unit": "TFLOP/s", "frac": round(ach / peak, 4), "traffic": None,
+    traffic, traffic_note = None, None
+    try:   # DRAM bytes per launch from the committed ncu --set full capture of the same kernel (profiles/)
+        t = json.load(open(os.path.join(ROOT, "profiles", "gemm_traffic_r01.json")))
+        traffic, traffic_note = t["mean_dram_bytes_per_launch"], t["source"]
+    except Exception:
+        pass
+    return {"bound": "tensor", "kernel": "lv::gemm2::gemm2_bf16_kernel (tcgen05 cta_group::2, all %d GEMM launches of one step)" % len(rec),
+            "achieved": round(ach, 1), "peak": peak, "unit": "TFLOP/s", "frac": round(ach / peak, 4), "traffic": traffic,
+            "traffic_source": traffic_note, "flops_per_launch": tot_fl / max(1, len(rec)),
             "peak_source": which, "flops_per_step": tot_fl, "gemm_ms_per_step": round(tot_ms, 3)}
 
 

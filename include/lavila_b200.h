@@ -105,9 +105,11 @@ int lv_layernorm_bwd(const void* dy, int dy_is_bf16, int64_t lddy, const float* 
  *   mode 2 = causal (group = (caption, head):          L queries/keys, additive -inf upper triangle)
  *   rows = B * (1 + T*n) for modes 0/1 (token 0 of each clip is CLS), B * L for mode 2.
  * The group kernels write the patch-token rows; lv_cls_attn_* handle token 0 (the CLS query attends to all N tokens,
- * timesformer.py:119).  Backward call order for modes 0/1: lv_cls_attn_bwd -> lv_group_attn_bwd(accumulate_kv=1)
- * -> lv_cls_kv_finalize.  dcls_kv: fp32 [B, H, 2, 64] scratch (written by lv_cls_attn_bwd, accumulated by the group
- * kernel, consumed by finalize).
+ * timesformer.py:119).  Backward call order for modes 0/1 (dcls_kv: fp32 [B, H, 2, 64] scratch, ZEROED by the caller):
+ * lv_group_attn_bwd / lv_space_attn_bwd_tc (accumulate_kv=0: plain stores, CLS-key partials -> dcls_kv atomics)
+ * -> lv_cls_attn_bwd(accumulate=1: streams over all keys adding its contribution) -> lv_cls_kv_finalize.
+ * (The opposite order, cls first then group with accumulate_kv=1, is also supported but exposes the read-modify-write
+ * latency inside the tensor-core kernel: measured 3.8 ms vs 2.0 ms per launch.)
  * ---------------------------------------------------------------------------------------------- */
 int lv_group_attn_fwd(const void* qkv, int64_t ld_qkv, void* out, int64_t ld_out, float* lse, int mode, int B, int H,
                       int T, int n, int L, void* stream);
@@ -135,7 +137,8 @@ int lv_debug_set_buffer(void* buf);
 int lv_cls_attn_fwd(const void* qkv, int64_t ld_qkv, void* out, int64_t ld_out, float* lse, int B, int H, int N,
                     void* stream);
 int lv_cls_attn_bwd(const void* qkv, int64_t ld_qkv, const void* out, int64_t ld_out, const void* dout, int64_t ld_dout,
-                    const float* lse, void* dqkv, int64_t ld_dqkv, float* dcls_kv, int B, int H, int N, void* stream);
+                    const float* lse, void* dqkv, int64_t ld_dqkv, float* dcls_kv, int accumulate, int B, int H, int N,
+                    void* stream);
 int lv_cls_kv_finalize(const float* dcls_kv, void* dqkv, int64_t ld_dqkv, int B, int H, int N, void* stream);
 /* CLS query attention with separate operands: q bf16 [B, D], kv bf16 [B*N, 2D] = [k | v], out bf16 [B, D], lse [B, H].
  * Used by the last SpaceTimeBlock, of which only the CLS row is consumed (timesformer.py:376-378). */

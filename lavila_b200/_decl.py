@@ -13,7 +13,7 @@ SIGNATURES = {
     "lv_flash_attn_fwd": [P, L, L, P, P, L, L, I, P, L, I, I, I, I, I, F, P],
     "lv_debug_set_buffer": [P],
     "lv_cls_attn_fwd": [P, L, P, L, P, I, I, I, P],
-    "lv_cls_attn_bwd": [P, L, P, L, P, L, P, P, L, P, I, I, I, P],
+    "lv_cls_attn_bwd": [P, L, P, L, P, L, P, P, L, P, I, I, I, I, P],
     "lv_cls_kv_finalize": [P, P, L, I, I, I, P],
     "lv_cls_query_attn_fwd": [P, P, P, P, I, I, I, P],
     "lv_cls_query_attn_bwd": [P, P, P, P, P, P, P, I, I, I, P],

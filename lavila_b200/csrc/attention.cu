@@ -571,6 +571,7 @@ struct ClsAddr {
   __nv_bfloat16 *dq, *dk, *dv;
   long long dq_bs, ld_dkv;
   float* dcls_kv;       // when non-null the CLS key/value row (j = 0) goes here in fp32 instead of dk/dv row 0
+  int accumulate;       // add to what is already in dk / dv / dcls_kv (the group backward ran first)
 };
 
 __global__ void __launch_bounds__(CLS_THREADS)
@@ -664,10 +665,22 @@ cls_attn_bwd_kernel(const ClsAddr a, int H, int N, float scale) {
       }
       if (j == 0 && a.dcls_kv) {
         float* kb = a.dcls_kv + ((long long)b * H + h) * 2 * HD + c * 8;
+        if (a.accumulate) {
 #pragma unroll
-        for (int e = 0; e < 8; ++e) { kb[e] = dk[e]; kb[HD + e] = dv[e]; }
+          for (int e = 0; e < 8; ++e) { kb[e] += dk[e]; kb[HD + e] += dv[e]; }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) { kb[e] = dk[e]; kb[HD + e] = dv[e]; }
+        }
       } else {
         const long long doff = (row0 + j) * a.ld_dkv + h * HD + c * 8;
+        if (a.accumulate) {   // streaming read-modify-write: the group backward has already written its part
+          float ok_[8], ov_[8];
+          unpack8(*reinterpret_cast<const uint4*>(a.dk + doff), ok_);
+          unpack8(*reinterpret_cast<const uint4*>(a.dv + doff), ov_);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) { dk[e] += ok_[e]; dv[e] += ov_[e]; }
+        }
         *reinterpret_cast<uint4*>(a.dk + doff) = make_uint4(pack_bf16x2(dk[0], dk[1]), pack_bf16x2(dk[2], dk[3]),
                                                             pack_bf16x2(dk[4], dk[5]), pack_bf16x2(dk[6], dk[7]));
         *reinterpret_cast<uint4*>(a.dv + doff) = make_uint4(pack_bf16x2(dv[0], dv[1]), pack_bf16x2(dv[2], dv[3]),
@@ -817,8 +830,8 @@ extern "C" int lv_cls_attn_fwd(const void* qkv, int64_t ld_qkv, void* out, int64
 }
 
 extern "C" int lv_cls_attn_bwd(const void* qkv, int64_t ld_qkv, const void* out, int64_t ld_out, const void* dout,
-                               int64_t ld_dout, const float* lse, void* dqkv, int64_t ld_dqkv, float* dcls_kv, int B, int H,
-                               int N, void* stream) {
+                               int64_t ld_dout, const float* lse, void* dqkv, int64_t ld_dqkv, float* dcls_kv, int accumulate,
+                               int B, int H, int N, void* stream) {
   LV_REQUIRE(qkv && out && dout && lse && dqkv && dcls_kv && B > 0 && H > 0 && N > 0, "lv_cls_attn_bwd: bad arguments");
   LV_REQUIRE(ld_qkv % 8 == 0 && ld_dqkv % 8 == 0, "lv_cls_attn_bwd: leading dimensions must be multiples of 8");
   attn::ClsAddr a{};
@@ -830,6 +843,7 @@ extern "C" int lv_cls_attn_bwd(const void* qkv, int64_t ld_qkv, const void* out,
   a.dout = (const __nv_bfloat16*)dout; a.do_bs = (long long)N * ld_dout;
   a.dq = dbase; a.dq_bs = (long long)N * ld_dqkv; a.dk = dbase + D; a.dv = dbase + 2 * D; a.ld_dkv = ld_dqkv;
   a.dcls_kv = dcls_kv;
+  a.accumulate = accumulate;
   attn::cls_attn_bwd_kernel<<<B * H, attn::CLS_THREADS, 0, (cudaStream_t)stream>>>(a, H, N, 0.125f);
   return check_launch("lv_cls_attn_bwd");
 }

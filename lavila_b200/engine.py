@@ -126,9 +126,11 @@ def attn_sub_bwd(dy, dy_b, P, S, adds=(), want_bf16=True):
     if mode == MODE_CAUSAL:
         ops.group_attn_bwd(S["qkv"], S["att"], S["lse"], datt, dqkv, None, 0, mode, B, H, Lctx=dims["L"])
     else:
-        dcls = torch.empty(B, H, 2, 64, device=dev, dtype=F32)
-        ops.cls_attn_bwd(S["qkv"], S["att"], datt, S["lse"], dqkv, dcls, B, H, dims["N"])
-        ops.group_attn_bwd(S["qkv"], S["att"], S["lse"], datt, dqkv, dcls, 1, mode, B, H, T=dims["T"], n=dims["n"])
+        # group kernel first (plain stores), then the streaming CLS-query kernel accumulates on top: keeps the
+        # read-modify-write latency out of the tensor-core kernel's critical path
+        dcls = torch.zeros(B, H, 2, 64, device=dev, dtype=F32)
+        ops.group_attn_bwd(S["qkv"], S["att"], S["lse"], datt, dqkv, dcls, 0, mode, B, H, T=dims["T"], n=dims["n"])
+        ops.cls_attn_bwd(S["qkv"], S["att"], datt, S["lse"], dqkv, dcls, B, H, dims["N"], accumulate=True)
         ops.cls_kv_finalize(dcls, dqkv, B, H, dims["N"])
     del datt
     # ---- qkv
@@ -659,9 +661,9 @@ class VarAttentionFn(torch.autograd.Function):
         datt = torch.empty(M, D, device=dev, dtype=BF16)
         ops.gemm(dyb, SHADOW.get(proj_w), M, D, D, datt, b_mn=1)
         dqkv = torch.empty(M, 3 * D, device=dev, dtype=BF16)
-        dcls = torch.empty(B, heads, 2, 64, device=dev, dtype=F32)
-        ops.cls_attn_bwd(qkv, att, datt, lse, dqkv, dcls, B, heads, N)
-        ops.group_attn_bwd(qkv, att, lse, datt, dqkv, dcls, 1, mode, B, heads, T=frames, n=patches)
+        dcls = torch.zeros(B, heads, 2, 64, device=dev, dtype=F32)
+        ops.group_attn_bwd(qkv, att, lse, datt, dqkv, dcls, 0, mode, B, heads, T=frames, n=patches)
+        ops.cls_attn_bwd(qkv, att, datt, lse, dqkv, dcls, B, heads, N, accumulate=True)
         ops.cls_kv_finalize(dcls, dqkv, B, heads, N)
         d_qw, d_qb = _zeros_like_param(qkv_w), _zeros_like_param(qkv_b)
         _wgrad(dqkv, xb, 3 * D, D, M, d_qw)

@@ -121,10 +121,10 @@ def cls_attn_fwd(qkv, out, lse, B, H, N):
     L.check(rc, "lv_cls_attn_fwd")
 
 
-def cls_attn_bwd(qkv, out, dout, lse, dqkv, dcls_kv, B, H, N):
+def cls_attn_bwd(qkv, out, dout, lse, dqkv, dcls_kv, B, H, N, accumulate=False):
     rc = L.lib().lv_cls_attn_bwd(qkv.data_ptr(), qkv.stride(0), out.data_ptr(), out.stride(0), dout.data_ptr(),
-                                 dout.stride(0), lse.data_ptr(), dqkv.data_ptr(), dqkv.stride(0), dcls_kv.data_ptr(), B,
-                                 H, N, _stream())
+                                 dout.stride(0), lse.data_ptr(), dqkv.data_ptr(), dqkv.stride(0), dcls_kv.data_ptr(),
+                                 int(accumulate), B, H, N, _stream())
     L.check(rc, "lv_cls_attn_bwd")
 
 
