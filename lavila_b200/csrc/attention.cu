@@ -583,25 +583,35 @@ cls_attn_fwd_kernel(const ClsAddr a, int H, int N, float scale) {
   float q[8];
   unpack8(__ldg(reinterpret_cast<const uint4*>(a.q + b * a.q_bs + h * HD + c * 8)), q);
   float m = -INFINITY, l = 0.f, acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  const int iters = (N + CLS_GROUPS - 1) / CLS_GROUPS;
+  constexpr int UNR = 4;   // keys in flight per thread: the pass is HBM-latency-bound otherwise
+  const int iters = (N + CLS_GROUPS * UNR - 1) / (CLS_GROUPS * UNR);
   for (int it = 0; it < iters; ++it) {
-    const int j = it * CLS_GROUPS + grp;
-    const bool ok = j < N;
-    const long long roff = (row0 + (ok ? j : 0)) * a.ld_kv + h * HD + c * 8;
-    float k[8], v[8];
-    unpack8(__ldg(reinterpret_cast<const uint4*>(a.k + roff)), k);
-    unpack8(__ldg(reinterpret_cast<const uint4*>(a.v + roff)), v);
-    float sp = 0.f;
+    uint4 kr[UNR], vr[UNR];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) sp += q[e] * k[e];
-    const float sc = oct_sum(sp) * scale;
-    if (ok) {
-      const float mn = fmaxf(m, sc);
-      const float corr = __expf(m - mn), pj = __expf(sc - mn);
-      l = l * corr + pj;
+    for (int u = 0; u < UNR; ++u) {
+      const int j = (it * UNR + u) * CLS_GROUPS + grp;
+      const long long roff = (row0 + (j < N ? j : 0)) * a.ld_kv + h * HD + c * 8;
+      kr[u] = __ldg(reinterpret_cast<const uint4*>(a.k + roff));
+      vr[u] = __ldg(reinterpret_cast<const uint4*>(a.v + roff));
+    }
 #pragma unroll
-      for (int e = 0; e < 8; ++e) acc[e] = acc[e] * corr + pj * v[e];
-      m = mn;
+    for (int u = 0; u < UNR; ++u) {
+      const int j = (it * UNR + u) * CLS_GROUPS + grp;
+      float k[8], v[8];
+      unpack8(kr[u], k);
+      unpack8(vr[u], v);
+      float sp = 0.f;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) sp += q[e] * k[e];
+      const float sc = oct_sum(sp) * scale;
+      if (j < N) {
+        const float mn = fmaxf(m, sc);
+        const float corr = __expf(m - mn), pj = __expf(sc - mn);
+        l = l * corr + pj;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] = acc[e] * corr + pj * v[e];
+        m = mn;
+      }
     }
   }
   if (c == 0) { s_m[grp] = m; s_l[grp] = l; }
@@ -640,51 +650,67 @@ cls_attn_bwd_kernel(const ClsAddr a, int H, int N, float scale) {
   const float delta = oct_sum(dpart);
   const float L = a.lse[b * a.l_bs + h];
   float dq[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  const int iters = (N + CLS_GROUPS - 1) / CLS_GROUPS;
+  constexpr int UNR = 4;
+  const int iters = (N + CLS_GROUPS * UNR - 1) / (CLS_GROUPS * UNR);
   for (int it = 0; it < iters; ++it) {
-    const int j = it * CLS_GROUPS + grp;
-    const bool ok = j < N;
-    const long long roff = (row0 + (ok ? j : 0)) * a.ld_kv + h * HD + c * 8;
-    float k[8], v[8];
-    unpack8(__ldg(reinterpret_cast<const uint4*>(a.k + roff)), k);
-    unpack8(__ldg(reinterpret_cast<const uint4*>(a.v + roff)), v);
-    float sp = 0.f, dpp = 0.f;
+    uint4 kr[UNR], vr[UNR], okr[UNR], ovr[UNR];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) { sp += q[e] * k[e]; dpp += dO[e] * v[e]; }
-    const float sc = oct_sum(sp) * scale;
-    const float dpj = oct_sum(dpp);
-    if (ok) {
-      const float pj = __expf(sc - L);
-      const float dsj = pj * (dpj - delta) * scale;   // d loss / d (q.k_j)
-      float dk[8], dv[8];
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        dq[e] += dsj * k[e];
-        dk[e] = dsj * q[e];
-        dv[e] = pj * dO[e];
+    for (int u = 0; u < UNR; ++u) {
+      const int j = (it * UNR + u) * CLS_GROUPS + grp;
+      const long long jj = row0 + (j < N ? j : 0);
+      const long long roff = jj * a.ld_kv + h * HD + c * 8;
+      kr[u] = __ldg(reinterpret_cast<const uint4*>(a.k + roff));
+      vr[u] = __ldg(reinterpret_cast<const uint4*>(a.v + roff));
+      if (a.accumulate) {
+        const long long doff = jj * a.ld_dkv + h * HD + c * 8;
+        okr[u] = *reinterpret_cast<const uint4*>(a.dk + doff);
+        ovr[u] = *reinterpret_cast<const uint4*>(a.dv + doff);
       }
-      if (j == 0 && a.dcls_kv) {
-        float* kb = a.dcls_kv + ((long long)b * H + h) * 2 * HD + c * 8;
-        if (a.accumulate) {
+    }
 #pragma unroll
-          for (int e = 0; e < 8; ++e) { kb[e] += dk[e]; kb[HD + e] += dv[e]; }
+    for (int u = 0; u < UNR; ++u) {
+      const int j = (it * UNR + u) * CLS_GROUPS + grp;
+      float k[8], v[8];
+      unpack8(kr[u], k);
+      unpack8(vr[u], v);
+      float sp = 0.f, dpp = 0.f;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { sp += q[e] * k[e]; dpp += dO[e] * v[e]; }
+      const float sc = oct_sum(sp) * scale;
+      const float dpj = oct_sum(dpp);
+      if (j < N) {
+        const float pj = __expf(sc - L);
+        const float dsj = pj * (dpj - delta) * scale;   // d loss / d (q.k_j)
+        float dk[8], dv[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          dq[e] += dsj * k[e];
+          dk[e] = dsj * q[e];
+          dv[e] = pj * dO[e];
+        }
+        if (j == 0 && a.dcls_kv) {
+          float* kb = a.dcls_kv + ((long long)b * H + h) * 2 * HD + c * 8;
+          if (a.accumulate) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { kb[e] += dk[e]; kb[HD + e] += dv[e]; }
+          } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { kb[e] = dk[e]; kb[HD + e] = dv[e]; }
+          }
         } else {
+          const long long doff = (row0 + j) * a.ld_dkv + h * HD + c * 8;
+          if (a.accumulate) {   // streaming read-modify-write: the group backward has already written its part
+            float ok_[8], ov_[8];
+            unpack8(okr[u], ok_);
+            unpack8(ovr[u], ov_);
 #pragma unroll
-          for (int e = 0; e < 8; ++e) { kb[e] = dk[e]; kb[HD + e] = dv[e]; }
+            for (int e = 0; e < 8; ++e) { dk[e] += ok_[e]; dv[e] += ov_[e]; }
+          }
+          *reinterpret_cast<uint4*>(a.dk + doff) = make_uint4(pack_bf16x2(dk[0], dk[1]), pack_bf16x2(dk[2], dk[3]),
+                                                              pack_bf16x2(dk[4], dk[5]), pack_bf16x2(dk[6], dk[7]));
+          *reinterpret_cast<uint4*>(a.dv + doff) = make_uint4(pack_bf16x2(dv[0], dv[1]), pack_bf16x2(dv[2], dv[3]),
+                                                              pack_bf16x2(dv[4], dv[5]), pack_bf16x2(dv[6], dv[7]));
         }
-      } else {
-        const long long doff = (row0 + j) * a.ld_dkv + h * HD + c * 8;
-        if (a.accumulate) {   // streaming read-modify-write: the group backward has already written its part
-          float ok_[8], ov_[8];
-          unpack8(*reinterpret_cast<const uint4*>(a.dk + doff), ok_);
-          unpack8(*reinterpret_cast<const uint4*>(a.dv + doff), ov_);
-#pragma unroll
-          for (int e = 0; e < 8; ++e) { dk[e] += ok_[e]; dv[e] += ov_[e]; }
-        }
-        *reinterpret_cast<uint4*>(a.dk + doff) = make_uint4(pack_bf16x2(dk[0], dk[1]), pack_bf16x2(dk[2], dk[3]),
-                                                            pack_bf16x2(dk[4], dk[5]), pack_bf16x2(dk[6], dk[7]));
-        *reinterpret_cast<uint4*>(a.dv + doff) = make_uint4(pack_bf16x2(dv[0], dv[1]), pack_bf16x2(dv[2], dv[3]),
-                                                            pack_bf16x2(dv[4], dv[5]), pack_bf16x2(dv[6], dv[7]));
       }
     }
   }

@@ -65,7 +65,7 @@ ops.cls_attn_fwd(qkv, out, lse, B, H, N)
 dout = torch.randn(M, D, device=dev).bfloat16()
 dqkv = torch.zeros(M, 3 * D, device=dev, dtype=torch.bfloat16)
 dcls = torch.zeros(B, H, 2, 64, device=dev)
-report("cls attn bwd", timeit(lambda: ops.cls_attn_bwd(qkv, out, dout, lse, dqkv, dcls, B, H, N)), 4 * u)
+report("cls attn bwd (accumulate)", timeit(lambda: ops.cls_attn_bwd(qkv, out, dout, lse, dqkv, dcls, B, H, N, accumulate=True)), 6 * u)
 if ONLY == "time_bwd":
     ops.group_attn_bwd(qkv, out, lse, dout, dqkv, dcls, 1, 1, B, H, T=T, n=n)
     torch.cuda.synchronize()
