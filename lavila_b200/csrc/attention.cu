@@ -16,6 +16,7 @@
 #include "../../include/lavila_b200.h"
 #include "host_common.h"
 #include "ptx.cuh"
+#include <stdlib.h>
 
 namespace lv {
 namespace attn {
@@ -741,6 +742,12 @@ using namespace lv;
 
 namespace {
 
+// LV_TIME_ATTN_GENERIC=1 routes time attention through the generic group kernels (A/B measurements only)
+bool generic_time_attn() {
+  static const bool v = [] { const char* e = getenv("LV_TIME_ATTN_GENERIC"); return e && e[0] == '1'; }();
+  return v;
+}
+
 // mode: 0 = space, 1 = time, 2 = causal text
 int fill_params(attn::Params& p, int mode, int B, int H, int T, int n, int L) {
   p.H = H;
@@ -785,6 +792,8 @@ extern "C" int lv_group_attn_fwd(const void* qkv, int64_t ld_qkv, void* out, int
                                  int H, int T, int n, int L, void* stream) {
   LV_REQUIRE(qkv && out && lse && B > 0 && H > 0, "lv_group_attn_fwd: bad arguments");
   LV_REQUIRE(ld_qkv % 8 == 0 && ld_out % 8 == 0, "lv_group_attn_fwd: leading dimensions must be multiples of 8");
+  if (mode == 1 && T <= 16 && !generic_time_attn())
+    return time_attn_small_fwd(qkv, ld_qkv, out, ld_out, lse, B, H, T, n, (cudaStream_t)stream);
   attn::Params p{};
   int rc = fill_params(p, mode, B, H, T, n, L);
   if (rc) return rc;
@@ -804,6 +813,10 @@ extern "C" int lv_group_attn_bwd(const void* qkv, int64_t ld_qkv, const void* ou
                                  int accumulate_kv, int mode, int B, int H, int T, int n, int L, void* stream) {
   LV_REQUIRE(qkv && out && lse && dout && dqkv && B > 0 && H > 0, "lv_group_attn_bwd: bad arguments");
   LV_REQUIRE(ld_qkv % 8 == 0 && ld_out % 8 == 0 && ld_dout % 8 == 0 && ld_dqkv % 8 == 0, "lv_group_attn_bwd: leading dimensions must be multiples of 8");
+  if (mode == 1 && T <= 16 && !accumulate_kv && !generic_time_attn()) {
+    LV_REQUIRE(dcls_kv, "lv_group_attn_bwd: dcls_kv required for CLS modes");
+    return time_attn_small_bwd(qkv, ld_qkv, out, ld_out, lse, dout, ld_dout, dqkv, ld_dqkv, dcls_kv, B, H, T, n, (cudaStream_t)stream);
+  }
   attn::Params p{};
   int rc = fill_params(p, mode, B, H, T, n, L);
   if (rc) return rc;

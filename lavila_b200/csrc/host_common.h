@@ -20,6 +20,13 @@ int sm_count();                       // SMs of the current device (cached per d
 int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t inner, uint64_t rows, uint64_t ld,
                       uint32_t box_inner, uint32_t box_rows);
 
+// small-group time attention (attention_time.cu), dispatched from lv_group_attn_fwd / lv_group_attn_bwd (mode 1, T <= 16)
+int time_attn_small_fwd(const void* qkv, long long ld_qkv, void* out, long long ld_out, float* lse, int B, int H, int T, int n,
+                        cudaStream_t st);
+int time_attn_small_bwd(const void* qkv, long long ld_qkv, const void* out, long long ld_out, const float* lse, const void* dout,
+                        long long ld_dout, void* dqkv, long long ld_dqkv, float* dcls_kv, int B, int H, int T, int n,
+                        cudaStream_t st);
+
 }  // namespace lv
 
 #define LV_REQUIRE(cond, ...)                                  \

@@ -129,7 +129,8 @@ def _attn_case(mode, B, H, T, n, seed):
 
 
 @pytest.mark.parametrize("mode,B,H,T,n", [("space", 2, 2, 4, 4), ("time", 2, 2, 4, 4), ("space", 1, 3, 2, 196),
-                                          ("time", 1, 3, 16, 9), ("space", 2, 12, 16, 196), ("time", 2, 12, 16, 196)])
+                                          ("time", 1, 3, 16, 9), ("space", 2, 12, 16, 196), ("time", 2, 12, 16, 196),
+                                          ("time", 2, 16, 8, 5), ("time", 3, 12, 16, 49)])
 def test_var_attention(mode, B, H, T, n):
     _attn_case(mode, B, H, T, n, seed=3)
 
