@@ -337,11 +337,15 @@ static_assert(FWD_SMEM <= 227 * 1024, "space attention forward: shared memory bu
 __device__ long long* g_dbg = nullptr;   // optional cycle-stamp buffer (lv_debug_set_buffer), CTA 0 only
 #define LV_STAMP(slot) do { if (g_dbg && blockIdx.x == 0 && it < 4) g_dbg[it * 64 + (slot)] = clock64(); } while (0)
 
-constexpr int B_ROWS = 256;
-constexpr int B_TILE_BYTES = B_ROWS * 128;    // Q, K, V, dO tiles (rows beyond n / n+1 stay zero)
+constexpr int B_ROWS = 208;                   // operand tile rows (n + 1 <= 208).  M = 128 operands of the second key tile
+                                              // read 48 rows past the tile into the next buffer: finite bf16, masked keys
+constexpr int B_TILE_BYTES = B_ROWS * 128;    // 26 KB, a multiple of the 1024-byte swizzle atom
+constexpr int B_NBUF = 6;                     // Q, K, V, dO of the current group + K, V of the next one
 constexpr int B_STAGE_BYTES = 2 * 128 * 128;  // P^T / dS^T: 128 key rows x 128 query columns (2 atoms of 64)
+constexpr int B_VEC = 256;                    // lse / delta entries per stage
 constexpr int TB_ST = 0, TB_DPT = 128, TB_DV = 256, TB_DK = 320, TB_DQ = 384;
-constexpr int BWD_SMEM = 1024 + 4 * B_TILE_BYTES + 2 * B_STAGE_BYTES + 2 * B_ROWS * 4 + 128;
+constexpr int BWD_SMEM = 1024 + B_NBUF * B_TILE_BYTES + 2 * B_STAGE_BYTES + 2 * 2 * B_VEC * 4 + 128;
+static_assert(B_TILE_BYTES % 1024 == 0, "tiles must keep the 1024-byte swizzle alignment");
 static_assert(BWD_SMEM <= 227 * 1024, "space attention backward: shared memory budget");
 
 struct BwdParams {
@@ -399,34 +403,59 @@ __device__ __forceinline__ void store_row64(__nv_bfloat16* dst, const uint32_t (
   }
 }
 
+// Same row as bf16 into a 128B-swizzled [rows x 64] staging tile that a TMA store then writes out.
+__device__ __forceinline__ void stage_row64(uint32_t tile, int row, const uint32_t (&a)[32], const uint32_t (&b)[32]) {
+#pragma unroll
+  for (int jj = 0; jj < 8; ++jj) {
+    const uint32_t* src = jj < 4 ? &a[jj * 8] : &b[(jj - 4) * 8];
+    st_shared_v4(tile + row * 128 + ((jj ^ (row & 7)) << 4),
+                 pack_bf16x2(__uint_as_float(src[0]), __uint_as_float(src[1])), pack_bf16x2(__uint_as_float(src[2]), __uint_as_float(src[3])),
+                 pack_bf16x2(__uint_as_float(src[4]), __uint_as_float(src[5])), pack_bf16x2(__uint_as_float(src[6]), __uint_as_float(src[7])));
+  }
+}
+
+// Pipeline across groups (one CTA walks groups it = 0, 1, ...):
+//   * operand tiles live in 6 rotating buffers, role r of group `it` in buffer (4*it + r) % 6 with r = 0:K 1:V 2:Q 3:dO.
+//     K and V of group it+1 therefore land in the two buffers group `it` does not use and are requested while it
+//     computes; Q and dO reuse the K/V buffers of group it-1 and are requested when its last MMA has retired.
+//   * lse (log2 units) and delta = rowsum(dO * O) of group it+1 are produced by the otherwise idle producer warp
+//     during group `it` into the other half of a two-stage buffer.
+//   * gradients leave through the (then free) P^T / dS^T staging tiles and TMA stores, not per-thread row stores.
 __global__ void __launch_bounds__(NTHREADS, 1)
 space_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
+                         const __grid_constant__ CUtensorMap tm_st128, const __grid_constant__ CUtensorMap tm_sttail,
                          const BwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* sQ = smem;
-  uint8_t* sK = sQ + B_TILE_BYTES;
-  uint8_t* sV = sK + B_TILE_BYTES;
-  uint8_t* sdO = sV + B_TILE_BYTES;
-  uint8_t* sPt = sdO + B_TILE_BYTES;
+  uint8_t* tiles = smem;
+  uint8_t* sPt = tiles + B_NBUF * B_TILE_BYTES;
   uint8_t* sdSt = sPt + B_STAGE_BYTES;
-  float* s_lse = reinterpret_cast<float*>(sdSt + B_STAGE_BYTES);
-  float* s_delta = s_lse + B_ROWS;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_delta + B_ROWS);
-  uint64_t* bar_load = bars;
-  uint64_t* bar_sdp = bars + 1;
-  uint64_t* bar_pds = bars + 2;
-  uint64_t* bar_mma3 = bars + 3;
-  uint64_t* bar_free = bars + 4;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+  float* s_lse = reinterpret_cast<float*>(sdSt + B_STAGE_BYTES);   // [2][B_VEC]
+  float* s_delta = s_lse + 2 * B_VEC;                               // [2][B_VEC]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_delta + 2 * B_VEC);
+  uint64_t* bar_loadA = bars;        // [2]  K, V landed (group parity selects the barrier)
+  uint64_t* bar_loadB = bars + 2;    //      Q, dO landed
+  uint64_t* bar_prep = bars + 3;     // [2]  lse / delta stage written
+  uint64_t* bar_sdp = bars + 5;
+  uint64_t* bar_pds = bars + 6;
+  uint64_t* bar_mma3 = bars + 7;
+  uint64_t* bar_free = bars + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int Lq = p.n, Lk = p.n + 1;
+  const bool tma_out = p.accumulate_kv == 0;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tm_qkv);
     prefetch_tmap(&tm_do);
-    mbar_init(bar_load, 1);
+    prefetch_tmap(&tm_st128);
+    prefetch_tmap(&tm_sttail);
+    mbar_init(&bar_loadA[0], 1);
+    mbar_init(&bar_loadA[1], 1);
+    mbar_init(bar_loadB, 1);
+    mbar_init(&bar_prep[0], 1);
+    mbar_init(&bar_prep[1], 1);
     mbar_init(bar_sdp, 1);
     mbar_init(bar_pds, 8);
     mbar_init(bar_mma3, 1);
@@ -437,43 +466,87 @@ space_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __gri
     tmem_alloc(tmem_slot, TMEM_COLS);
     tmem_relinquish();
   }
-  // zero once: padding rows of the operand tiles and both staging tiles
-  for (int idx = threadIdx.x; idx < (B_ROWS - Lq) * 8; idx += NTHREADS) {
-    st_shared_v4(smem_u32(sQ) + Lq * 128 + idx * 16, 0, 0, 0, 0);
-    st_shared_v4(smem_u32(sdO) + Lq * 128 + idx * 16, 0, 0, 0, 0);
-    st_shared_v4(smem_u32(sK) + Lq * 128 + idx * 16, 0, 0, 0, 0);
-    st_shared_v4(smem_u32(sV) + Lq * 128 + idx * 16, 0, 0, 0, 0);
-  }
-  for (int idx = threadIdx.x; idx < 2 * B_STAGE_BYTES / 16; idx += NTHREADS) st_shared_v4(smem_u32(sPt) + idx * 16, 0, 0, 0, 0);
+  // zero once: every tile buffer (padding rows are never written again; over-read rows must be finite), both
+  // staging tiles and the lse / delta stages (entries >= n are read as padding columns)
+  for (int idx = threadIdx.x; idx < (B_NBUF * B_TILE_BYTES + 2 * B_STAGE_BYTES + 2 * 2 * B_VEC * 4) / 16; idx += NTHREADS)
+    st_shared_v4(smem_u32(tiles) + idx * 16, 0, 0, 0, 0);
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  auto tile_of = [&](int it, int r) -> uint8_t* { return tiles + ((4 * (it % 3) + r) % B_NBUF) * B_TILE_BYTES; };
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ producer
-    int it = 0;
-    for (long long g = blockIdx.x; g < p.num_groups; g += gridDim.x, ++it) {
-      if (it > 0) {
-        if (lane == 0) mbar_wait(bar_free, (it - 1) & 1);  // every MMA of the previous group has read its operands
-        __syncwarp();
-      }
-      const Coord c = decode(p, g);
-      if (lane < 16) {
+    // ------------------------------------------------------------------ producer (+ lse / delta of the next group)
+    auto issue_kv = [&](int it2, const Coord& c) {
+      uint8_t* bk = tile_of(it2, 0);
+      uint8_t* bv = tile_of(it2, 1);
+      if (lane < 16) {   // the CLS key / value row closes the tile
         const int part = lane >> 3, ch = lane & 7;
         const uint4 v = __ldg(reinterpret_cast<const uint4*>(p.qkv + c.cls_row * p.ld_qkv + (1 + part) * p.D + c.h * HD + ch * 8));
-        st_shared_v4(smem_u32(part ? sV : sK) + Lq * 128 + ((ch ^ (Lq & 7)) << 4), v.x, v.y, v.z, v.w);
+        st_shared_v4(smem_u32(part ? bv : bk) + Lq * 128 + ((ch ^ (Lq & 7)) << 4), v.x, v.y, v.z, v.w);
       }
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) {
-        mbar_arrive_expect_tx(bar_load, 4 * Lq * 128);
-        tma_load_2d(sQ, &tm_qkv, bar_load, c.h * HD, (int)c.base_row);
-        tma_load_2d(sK, &tm_qkv, bar_load, p.D + c.h * HD, (int)c.base_row);
-        tma_load_2d(sV, &tm_qkv, bar_load, 2 * p.D + c.h * HD, (int)c.base_row);
-        tma_load_2d(sdO, &tm_do, bar_load, c.h * HD, (int)c.base_row);
+        uint64_t* bar = &bar_loadA[it2 & 1];
+        mbar_arrive_expect_tx(bar, 2 * Lq * 128);
+        tma_load_2d(bk, &tm_qkv, bar, p.D + c.h * HD, (int)c.base_row);
+        tma_load_2d(bv, &tm_qkv, bar, 2 * p.D + c.h * HD, (int)c.base_row);
       }
+    };
+    auto issue_qdo = [&](int it2, const Coord& c) {
+      if (lane == 0) {
+        mbar_arrive_expect_tx(bar_loadB, 2 * Lq * 128);
+        tma_load_2d(tile_of(it2, 2), &tm_qkv, bar_loadB, c.h * HD, (int)c.base_row);
+        tma_load_2d(tile_of(it2, 3), &tm_do, bar_loadB, c.h * HD, (int)c.base_row);
+      }
+    };
+    auto prep = [&](int it2, const Coord& c) {
+      float* ls = s_lse + (it2 & 1) * B_VEC;
+      float* dl = s_delta + (it2 & 1) * B_VEC;
+#pragma unroll 1
+      for (int r = lane; r < Lq; r += 32) {
+        const long long grow = c.base_row + r;
+        const __nv_bfloat16* orow = p.out + grow * p.ld_out + c.h * HD;
+        const __nv_bfloat16* drow = p.dout + grow * p.ld_dout + c.h * HD;
+        uint4 o8[8], d8[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          o8[j] = __ldg(reinterpret_cast<const uint4*>(orow + j * 8));
+          d8[j] = __ldg(reinterpret_cast<const uint4*>(drow + j * 8));
+        }
+        const float l2 = __ldg(p.lse + grow * p.H + c.h) * LOG2E;
+        float acc = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc += dot8(o8[j], d8[j]);
+        ls[r] = l2;
+        dl[r] = acc;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_prep[it2 & 1]);
+    };
+    long long g = blockIdx.x;
+    if (g < p.num_groups) {
+      const Coord c = decode(p, g);
+      issue_kv(0, c);
+      issue_qdo(0, c);
+      prep(0, c);
+    }
+    int it = 0;
+    for (; g < p.num_groups; g += gridDim.x, ++it) {
+      const long long gn = g + gridDim.x;
+      const bool has_next = gn < p.num_groups;
+      Coord cn{};
+      if (has_next) {
+        cn = decode(p, gn);
+        issue_kv(it + 1, cn);   // buffers of group it-1's Q / dO: free since bar_free(it-1)
+        prep(it + 1, cn);
+      }
+      if (lane == 0) mbar_wait(bar_free, it & 1);   // every MMA of group `it` has read its operands
+      __syncwarp();
+      if (has_next) issue_qdo(it + 1, cn);          // buffers of group it's K / V
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
@@ -482,7 +555,6 @@ space_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __gri
       constexpr uint32_t HI = (1024u >> 4) | (1u << 14) | (2u << 29);      // SBO 1024 B, version 1, SWIZZLE_128B
       auto dk = [](uint32_t addr) -> uint64_t { return ((uint64_t)HI << 32) | (uint32_t)(((addr & 0x3FFFFu) >> 4) | (1u << 16)); };           // K-major
       auto dmn = [](uint32_t addr, uint32_t lbo) -> uint64_t { return ((uint64_t)HI << 32) | (uint32_t)(((addr & 0x3FFFFu) >> 4) | ((lbo >> 4) << 16)); };  // MN-major
-      const uint32_t q_base = smem_u32(sQ), k_base = smem_u32(sK), v_base = smem_u32(sV), do_base = smem_u32(sdO);
       const uint32_t pt_base = smem_u32(sPt), ds_base = smem_u32(sdSt);
       constexpr uint32_t idesc_a128 = make_idesc_bf16(128, 128, 0, 0);
       constexpr uint32_t idesc_a80 = make_idesc_bf16(128, 80, 0, 0);
@@ -490,8 +562,11 @@ space_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __gri
       constexpr uint32_t idesc_dq = make_idesc_bf16(128, HD, 1, 1);   // A MN-major (dS^T read transposed), B MN-major
       int it = 0;
       for (long long g = blockIdx.x; g < p.num_groups; g += gridDim.x, ++it) {
+        const uint32_t k_base = smem_u32(tile_of(it, 0)), v_base = smem_u32(tile_of(it, 1));
+        const uint32_t q_base = smem_u32(tile_of(it, 2)), do_base = smem_u32(tile_of(it, 3));
         LV_STAMP(0);
-        mbar_wait(bar_load, it & 1);
+        mbar_wait(&bar_loadA[it & 1], (it >> 1) & 1);
+        mbar_wait(bar_loadB, it & 1);
         LV_STAMP(1);
         tc_fence_after();
         auto issue_a = [&](int step) {   // S^T = K_kt Q_qt^T ,  dP^T = V_kt dO_qt^T
@@ -538,51 +613,56 @@ space_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __gri
     // ------------------------------------------------------------------ elementwise + epilogue warps
     const int e = warp - 2, hf = e >> 2, q = warp & 3;
     const int row = q * 32 + lane;   // TMEM lane = key row inside the key tile (or query row for the dQ epilogue)
-    const int et = e * 32 + lane;    // 0..255
     const uint32_t trow = tmem_base + (uint32_t(q * 32) << 16);
     const float sl2 = p.scale * LOG2E;
+    const bool elected = warp == 2 && lane == 0;
+    const uint32_t pt_tile = smem_u32(sPt), ds_tile = smem_u32(sdSt);
     int it = 0;
     for (long long g = blockIdx.x; g < p.num_groups; g += gridDim.x, ++it) {
       const Coord c = decode(p, g);
-      // ---- per-query lse (in log2 units) and delta = sum_d dO*O
-      {
-        float l2 = 0.f, dl = 0.f;
-        if (et < Lq) {
-          const long long grow = c.base_row + et;
-          const __nv_bfloat16* orow = p.out + grow * p.ld_out + c.h * HD;
-          const __nv_bfloat16* drow = p.dout + grow * p.ld_dout + c.h * HD;
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            dl += dot8(__ldg(reinterpret_cast<const uint4*>(orow + j * 8)), __ldg(reinterpret_cast<const uint4*>(drow + j * 8)));
-          l2 = p.lse[grow * p.H + c.h] * LOG2E;
-        }
-        s_lse[et] = l2;
-        s_delta[et] = dl;
-      }
-      bar_sync_epi();
-      if (warp == 2 && lane == 0) LV_STAMP(20);
+      const float* lse_s = s_lse + (it & 1) * B_VEC;
+      const float* delta_s = s_delta + (it & 1) * B_VEC;
+      mbar_wait(&bar_prep[it & 1], (it >> 1) & 1);
+      if (elected) LV_STAMP(20);
 #pragma unroll 1
       for (int step = 0; step < 4; ++step) {
         const int kt = step >> 1, qt = step & 1;
         mbar_wait(bar_sdp, step & 1);
-        if (warp == 2 && lane == 0) LV_STAMP(21 + step * 4);
+        if (elected) LV_STAMP(21 + step * 4);
         if (step > 0) mbar_wait(bar_mma3, (step - 1) & 1);   // previous (B) MMAs have consumed the staged tiles
-        if (warp == 2 && lane == 0) LV_STAMP(22 + step * 4);
+        if (elected) LV_STAMP(22 + step * 4);
         tc_fence_after();
+        if (step == 0 && it > 0 && tma_out) {
+          // the stores of the previous group's last gradients must have read the staging tiles before they are rewritten
+          if (elected) tma_store_wait_read();
+          bar_sync_epi();
+        }
         if (step == 2) {
           // ---- epilogue of key tile 0: dV (hf 0) / dK (hf 1)
           uint32_t a[32], b[32];
           tmem_ld_32x32(trow + (hf ? TB_DK : TB_DV), a);
           tmem_ld_32x32(trow + (hf ? TB_DK : TB_DV) + 32, b);
           tmem_ld_wait();
-          const int key = row;   // < 128 <= Lq
-          store_row64(p.dqkv + (c.base_row + key) * p.ld_dqkv + (hf ? 1 : 2) * p.D + c.h * HD, a, b, p.accumulate_kv != 0);
+          if (tma_out) {
+            stage_row64(pt_tile + hf * 16384, row, a, b);
+            fence_proxy_async_smem();
+            bar_sync_epi();
+            if (elected) {
+              tma_store_2d(&tm_st128, sPt, 2 * p.D + c.h * HD, (int)c.base_row);
+              tma_store_2d(&tm_st128, sPt + 16384, p.D + c.h * HD, (int)c.base_row);
+              tma_store_commit();
+              tma_store_wait_read();
+            }
+            bar_sync_epi();
+          } else {
+            store_row64(p.dqkv + (c.base_row + row) * p.ld_dqkv + (hf ? 1 : 2) * p.D + c.h * HD, a, b, true);
+          }
         }
         const int key = kt * 128 + row;
         const bool key_ok = key < Lk;
         const int ncols = qt ? 40 : 64;         // this warp's share of the query columns
         const int col_base = hf * ncols;
-        const uint32_t pt_row = smem_u32(sPt) + row * 128, ds_row = smem_u32(sdSt) + row * 128;
+        const uint32_t pt_row = pt_tile + row * 128, ds_row = ds_tile + row * 128;
         // 32 columns per TMEM round trip (one wait per 32x2 values instead of per 8)
         for (int cb = 0; cb < ncols; cb += 32) {
           const int col0 = col_base + cb;       // query column inside the tile
@@ -605,8 +685,8 @@ space_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __gri
             if (g8 < ngroups) {
               const int c8 = col0 + g8 * 8;
               const int qg = qt * 128 + c8;
-              const float4 la = *reinterpret_cast<const float4*>(s_lse + qg), lb = *reinterpret_cast<const float4*>(s_lse + qg + 4);
-              const float4 da = *reinterpret_cast<const float4*>(s_delta + qg), db = *reinterpret_cast<const float4*>(s_delta + qg + 4);
+              const float4 la = *reinterpret_cast<const float4*>(lse_s + qg), lb = *reinterpret_cast<const float4*>(lse_s + qg + 4);
+              const float4 da = *reinterpret_cast<const float4*>(delta_s + qg), db = *reinterpret_cast<const float4*>(delta_s + qg + 4);
               const float l8[8] = {la.x, la.y, la.z, la.w, lb.x, lb.y, lb.z, lb.w};
               const float dl8[8] = {da.x, da.y, da.z, da.w, db.x, db.y, db.z, db.w};
               float pv[8], dv[8];
@@ -623,7 +703,7 @@ space_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __gri
                   const bool ok = key_ok && (qg + j < Lq);
                   const float pj = ok ? exp2f(fmaf(__uint_as_float(s32[g8 * 8 + j]), sl2, -l8[j])) : 0.f;
                   pv[j] = pj;
-                  dv[j] = pj * (__uint_as_float(d32[g8 * 8 + j]) - dl8[j]) * p.scale;
+                  dv[j] = ok ? pj * (__uint_as_float(d32[g8 * 8 + j]) - dl8[j]) * p.scale : 0.f;
                 }
               }
               const uint32_t off = (c8 >> 6) * 16384 + ((((c8 & 63) >> 3) ^ (row & 7)) << 4);
@@ -632,16 +712,16 @@ space_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __gri
             }
           }
         }
-        if (warp == 2 && lane == 0) LV_STAMP(23 + step * 4);
+        if (elected) LV_STAMP(23 + step * 4);
         fence_proxy_async_smem();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_pds);
-        if (warp == 2 && lane == 0) LV_STAMP(24 + step * 4);
+        if (elected) LV_STAMP(24 + step * 4);
       }
       // ---- final epilogues: key tile 1 (dV / dK) and dQ0 / dQ1
       mbar_wait(bar_mma3, 1);
-      if (warp == 2 && lane == 0) LV_STAMP(40);
+      if (elected) LV_STAMP(40);
       tc_fence_after();
       {
         uint32_t a[32], b[32];
@@ -649,9 +729,12 @@ space_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __gri
         tmem_ld_32x32(trow + (hf ? TB_DK : TB_DV) + 32, b);
         tmem_ld_wait();
         const int key = 128 + row;
-        if (key < Lq) {
-          store_row64(p.dqkv + (c.base_row + key) * p.ld_dqkv + (hf ? 1 : 2) * p.D + c.h * HD, a, b, p.accumulate_kv != 0);
-        } else if (key == Lq && p.dcls_kv) {  // CLS key / value: fp32 atomics into the per-(clip, head) accumulator
+        if (tma_out) {
+          stage_row64(pt_tile + hf * 16384, row, a, b);   // rows >= n - 128 are staged but lie outside the store box
+        } else if (key < Lq) {
+          store_row64(p.dqkv + (c.base_row + key) * p.ld_dqkv + (hf ? 1 : 2) * p.D + c.h * HD, a, b, true);
+        }
+        if (key == Lq && p.dcls_kv) {  // CLS key / value: fp32 atomics into the per-(clip, head) accumulator
           float* base = p.dcls_kv + (((long long)c.b * p.H + c.h) * 2 + (hf ? 0 : 1)) * HD;
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
@@ -666,12 +749,24 @@ space_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __gri
         tmem_ld_32x32(trow + TB_DQ + hf * 64 + 32, b);
         tmem_ld_wait();
         const int qrow = hf * 128 + row;
-        if (qrow < Lq) store_row64(p.dqkv + (c.base_row + qrow) * p.ld_dqkv + c.h * HD, a, b, false);
+        if (tma_out) stage_row64(ds_tile + hf * 16384, row, a, b);
+        else if (qrow < Lq) store_row64(p.dqkv + (c.base_row + qrow) * p.ld_dqkv + c.h * HD, a, b, false);
       }
-      if (warp == 2 && lane == 0) LV_STAMP(41);
       tc_fence_before();
-      bar_sync_epi();   // s_lse / s_delta of this group are dead; TMEM accumulators drained
+      if (tma_out) {
+        fence_proxy_async_smem();
+        bar_sync_epi();
+        if (elected) {
+          tma_store_2d(&tm_sttail, sPt, 2 * p.D + c.h * HD, (int)c.base_row + 128);           // dV keys 128..n-1
+          tma_store_2d(&tm_sttail, sPt + 16384, p.D + c.h * HD, (int)c.base_row + 128);       // dK
+          tma_store_2d(&tm_st128, sdSt, c.h * HD, (int)c.base_row);                           // dQ rows 0..127
+          tma_store_2d(&tm_sttail, sdSt + 16384, c.h * HD, (int)c.base_row + 128);            // dQ rows 128..n-1
+          tma_store_commit();
+        }
+      }
+      if (elected) LV_STAMP(41);
     }
+    if (elected && tma_out) tma_store_wait_all();
   }
   __syncthreads();
   if (warp == 1) {
@@ -740,6 +835,11 @@ extern "C" int lv_space_attn_bwd_tc(const void* qkv, int64_t ld_qkv, const void*
   if (rc) return rc;
   rc = make_tmap_2d_bf16(&tm_do, dout, (uint64_t)p.D, (uint64_t)rows, (uint64_t)ld_dout, 64, (uint32_t)n);
   if (rc) return rc;
+  CUtensorMap tm_st128, tm_sttail;   // gradient stores: 128-row boxes and the (n - 128)-row tail
+  rc = make_tmap_2d_bf16(&tm_st128, dqkv, (uint64_t)(3 * p.D), (uint64_t)rows, (uint64_t)ld_dqkv, 64, 128);
+  if (rc) return rc;
+  rc = make_tmap_2d_bf16(&tm_sttail, dqkv, (uint64_t)(3 * p.D), (uint64_t)rows, (uint64_t)ld_dqkv, 64, (uint32_t)(n - 128));
+  if (rc) return rc;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, []() {
@@ -747,7 +847,7 @@ extern "C" int lv_space_attn_bwd_tc(const void* qkv, int64_t ld_qkv, const void*
   });
   if (attr_err != cudaSuccess) return set_error((int)attr_err, "lv_space_attn_bwd_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err));
   const long long grid = p.num_groups < sm_count() ? p.num_groups : sm_count();
-  attn_tc::space_attn_bwd_tc_kernel<<<(unsigned)grid, attn_tc::NTHREADS, attn_tc::BWD_SMEM, (cudaStream_t)stream>>>(tm_qkv, tm_do, p);
+  attn_tc::space_attn_bwd_tc_kernel<<<(unsigned)grid, attn_tc::NTHREADS, attn_tc::BWD_SMEM, (cudaStream_t)stream>>>(tm_qkv, tm_do, tm_st128, tm_sttail, p);
   return check_launch("lv_space_attn_bwd_tc");
 }
 

@@ -50,16 +50,22 @@ if which == "fwd":
 else:
     dout = torch.randn(M, D, device=dev).bfloat16()
 
-    def run_bwd(tc):
+    def run_bwd(tc, group_first=True):
         ops.USE_TC_ATTN_BWD = tc
-        dqkv = torch.zeros(M, 3 * D, device=dev, dtype=torch.bfloat16)
+        dqkv = torch.full((M, 3 * D), 7.0, device=dev, dtype=torch.bfloat16)   # every element must be overwritten
         dcls = torch.zeros(B, H, 2, 64, device=dev)
-        ops.cls_attn_bwd(qkv, o_ref, dout, l_ref, dqkv, dcls, B, H, N)
-        ops.group_attn_bwd(qkv, o_ref, l_ref, dout, dqkv, dcls, 1, 0, B, H, T=T, n=n)
+        if group_first:   # the engine's order: plain writes, then the accumulating CLS-query pass
+            ops.group_attn_bwd(qkv, o_ref, l_ref, dout, dqkv, dcls, 0, 0, B, H, T=T, n=n)
+            ops.cls_attn_bwd(qkv, o_ref, dout, l_ref, dqkv, dcls, B, H, N, accumulate=True)
+        else:
+            ops.cls_attn_bwd(qkv, o_ref, dout, l_ref, dqkv, dcls, B, H, N)
+            ops.group_attn_bwd(qkv, o_ref, l_ref, dout, dqkv, dcls, 1, 0, B, H, T=T, n=n)
         ops.cls_kv_finalize(dcls, dqkv, B, H, N)
         torch.cuda.synchronize()
         return dqkv
     g_ref = run_bwd(False)
+    g2 = run_bwd(True, group_first=False)
+    print("bwd (cls first, accumulate path) rel %.3e" % rel(g2, g_ref))
     g = run_bwd(True)
     for nm, sl in (("dq", slice(0, D)), ("dk", slice(D, 2 * D)), ("dv", slice(2 * D, 3 * D))):
         print("bwd %s rel %.3e   cls-row rel %.3e" % (nm, rel(g[:, sl], g_ref[:, sl]), rel(g[::N, sl], g_ref[::N, sl])))
