@@ -192,6 +192,19 @@ int lv_clip_loss_bwd(const float* img, const float* txt, const float* scale_ptr,
                      const float* lse_txt, const float* gout, float grad_scale, float scale_grad_scale, int Ng, int E,
                      int r0, int Nl, float* d_img, float* d_txt, float* d_scale, void* stream);
 
+/* SSLCLIPLoss (lavila/models/loss.py:148-213): gt[i] = 1 human narration / 0 pseudo narration; pair scale
+ * c(i,j) = *scale_pseudo_ptr (0 + 0) | sqrt(*scale_pseudo_ptr * *scale_ptr) (0 + 1) | *scale_ptr (1 + 1), both pointers hold the
+ * already exponentiated scales.  result[6] = {loss, clip_acc, clip_acc_gt, clip_acc_pseudo, num_gt, num_pseudo} (an empty
+ * class gives NaN accuracy, as in the reference).  bwd: as lv_clip_loss_bwd; d_scales[2] (may be NULL) accumulates
+ * {d loss / d scale, d loss / d scale_pseudo} * scale_grad_scale over the local image rows. */
+int lv_ssl_clip_loss_fwd(const float* img, const float* txt, const float* scale_ptr, const float* scale_pseudo_ptr,
+                         const int32_t* gt, int Ng, int E, float* lse_img, float* lse_txt, float* partial, uint32_t* counter,
+                         float* result, void* stream);
+int lv_ssl_clip_loss_bwd(const float* img, const float* txt, const float* scale_ptr, const float* scale_pseudo_ptr,
+                         const int32_t* gt, const float* lse_img, const float* lse_txt, const float* gout, float grad_scale,
+                         float scale_grad_scale, int Ng, int E, int r0, int Nl, float* d_img, float* d_txt, float* d_scales,
+                         void* stream);
+
 #ifdef __cplusplus
 }
 #endif

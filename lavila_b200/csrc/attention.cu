@@ -805,7 +805,8 @@ extern "C" int lv_group_attn_fwd(const void* qkv, int64_t ld_qkv, void* out, int
   if (Lk <= 32) return launch_fwd<4>(p, st);
   if (Lk <= 80) return launch_fwd<10>(p, st);
   if (Lk <= 208) return launch_fwd<26>(p, st);
-  return set_error(-1, "lv_group_attn_fwd: %d keys per group not supported yet (max 208)", Lk);
+  LV_REQUIRE(mode != 2, "lv_group_attn_fwd: causal groups of %d keys not supported (max 208)", Lk);
+  return big_group_attn_fwd(qkv, ld_qkv, out, ld_out, lse, mode, B, H, T, n, st);   // TSF-L/14: 257 / 577 keys
 }
 
 extern "C" int lv_group_attn_bwd(const void* qkv, int64_t ld_qkv, const void* out, int64_t ld_out, const float* lse,
@@ -835,7 +836,11 @@ extern "C" int lv_group_attn_bwd(const void* qkv, int64_t ld_qkv, const void* ou
   p.staged = q_rows <= 32 ? 1 : 0;
   if (p.staged) per_group += q_rows * attn::ROW_BYTES + 2 * k_rows * attn::ROW_BYTES;
   p.group_bytes = per_group;
-  LV_REQUIRE(per_group + 512 <= 227 * 1024, "lv_group_attn_bwd: group with %d keys does not fit in shared memory", Lk);
+  if (per_group + 512 > 227 * 1024) {   // TSF-L/14 groups (257 / 577 keys): key-tiled kernels
+    LV_REQUIRE(mode != 2 && !accumulate_kv, "lv_group_attn_bwd: groups of %d keys need mode 0/1 and accumulate_kv = 0", Lk);
+    return big_group_attn_bwd(qkv, ld_qkv, out, ld_out, lse, dout, ld_dout, dqkv, ld_dqkv, dcls_kv, mode, B, H, T, n,
+                              (cudaStream_t)stream);
+  }
   int wg = (k_rows / 16 + 1) / 2;
   if (wg > 8) wg = 8;
   if (wg < 1) wg = 1;

@@ -201,6 +201,146 @@ clip_loss_bwd_kernel(const float* __restrict__ img, const float* __restrict__ tx
   }
 }
 
+// ================================================================================================ SSLCLIPLoss
+// lavila/models/loss.py:148-213: the LaViLa recipe's loss over human (gt = 1) and pseudo-narrated (gt = 0) pairs.
+//   logits[i,j] = c(i,j) * <I_i, T_j>,   c = s_p (both pseudo) | sqrt(s_p * s) (mixed) | s (both human)   (:160-164)
+// c is symmetric, so logits_per_text = logits^T (:165 / :178).  Same structure as the CLIPLoss kernels above.
+__device__ __forceinline__ float pair_scale(int gi, int gj, float s, float sp, float smix) {
+  const int m = gi + gj;
+  return m == 2 ? s : (m == 1 ? smix : sp);
+}
+
+// result[6] = {loss, acc, acc_gt, acc_pseudo, num_gt, num_pseudo};  partial [Ng][2] = {loss term, correct}.
+__global__ void __launch_bounds__(THREADS)
+ssl_clip_loss_fwd_kernel(const float* __restrict__ img, const float* __restrict__ txt, const float* __restrict__ scale_ptr,
+                         const float* __restrict__ scale_pseudo_ptr, const int* __restrict__ gt, int Ng, int E,
+                         float* __restrict__ lse_img, float* __restrict__ lse_txt, float* __restrict__ partial,
+                         unsigned int* __restrict__ counter, float* __restrict__ result) {
+  extern __shared__ float sm[];
+  float* a_img = sm;            // [E]
+  float* a_txt = sm + E;        // [E]
+  float* vals = sm + 2 * E;     // [Ng]
+  __shared__ float sred[THREADS / 32];
+  __shared__ int ired[THREADS / 32];
+  __shared__ bool is_last;
+  const int i = blockIdx.x, tid = threadIdx.x;
+  const float s = __ldg(scale_ptr), sp = __ldg(scale_pseudo_ptr), smix = sqrtf(sp * s);
+  const int gi = gt[i];
+  for (int c = tid; c < E; c += THREADS) {
+    a_img[c] = img[(long long)i * E + c];
+    a_txt[c] = txt[(long long)i * E + c];
+  }
+  __syncthreads();
+  for (int j = tid; j < Ng; j += THREADS) vals[j] = pair_scale(gi, gt[j], s, sp, smix) * dot_row(a_img, txt + (long long)j * E, E);
+  __syncthreads();
+  const RowStat ri = row_stats(vals, Ng, i, sred, ired);
+  __syncthreads();
+  for (int j = tid; j < Ng; j += THREADS) vals[j] = pair_scale(gi, gt[j], s, sp, smix) * dot_row(a_txt, img + (long long)j * E, E);
+  __syncthreads();
+  const RowStat rt = row_stats(vals, Ng, i, sred, ired);
+  if (tid == 0) {
+    lse_img[i] = ri.lse;
+    lse_txt[i] = rt.lse;
+    partial[2 * i] = 0.5f * ((ri.lse - ri.label_logit) + (rt.lse - rt.label_logit));
+    partial[2 * i + 1] = (ri.argmax == i) ? 1.f : 0.f;
+    __threadfence();
+    const unsigned int done = atomicAdd(counter, 1u);
+    is_last = (done == (unsigned)Ng - 1);
+  }
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    float v[4] = {0.f, 0.f, 0.f, 0.f};   // loss, correct, correct among gt, number of gt
+    for (int j = tid; j < Ng; j += THREADS) {
+      const float c = __ldcg(partial + 2 * j + 1);
+      const float isg = gt[j] == 1 ? 1.f : 0.f;
+      v[0] += __ldcg(partial + 2 * j);
+      v[1] += c;
+      v[2] += c * isg;
+      v[3] += isg;
+    }
+    __shared__ float red[4][THREADS / 32];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      v[k] = warp_sum(v[k]);
+      if ((tid & 31) == 0) red[k][tid >> 5] = v[k];
+    }
+    __syncthreads();
+    if (tid == 0) {
+      float t[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int k = 0; k < 4; ++k)
+        for (int w = 0; w < THREADS / 32; ++w) t[k] += red[k][w];
+      const float n_gt = t[3], n_ps = (float)Ng - t[3];
+      result[0] = t[0] / Ng;
+      result[1] = 100.f * t[1] / Ng;
+      result[2] = 100.f * t[2] / n_gt;              // 0/0 -> NaN, like the reference's empty-selection mean (:203-204)
+      result[3] = 100.f * (t[1] - t[2]) / n_ps;
+      result[4] = n_gt;
+      result[5] = n_ps;
+      *counter = 0;
+    }
+  }
+}
+
+// Same CTA mapping as clip_loss_bwd_kernel.  d_scales[0] += d loss / d s, d_scales[1] += d loss / d s_p (local image rows).
+__global__ void __launch_bounds__(THREADS)
+ssl_clip_loss_bwd_kernel(const float* __restrict__ img, const float* __restrict__ txt, const float* __restrict__ scale_ptr,
+                         const float* __restrict__ scale_pseudo_ptr, const int* __restrict__ gt,
+                         const float* __restrict__ lse_img, const float* __restrict__ lse_txt,
+                         const float* __restrict__ gout_ptr, float grad_scale, float scale_grad_scale, int Ng, int E, int r0,
+                         int Nl, float* __restrict__ d_img, float* __restrict__ d_txt, float* __restrict__ d_scales) {
+  extern __shared__ float sm[];
+  float* a_row = sm;          // [E]
+  float* w = sm + E;          // [Ng] dlogits * pair scale
+  __shared__ float sred[2][THREADS / 32];
+  const int tid = threadIdx.x;
+  const bool is_img = blockIdx.x < (unsigned)Nl;
+  const int i = r0 + (is_img ? blockIdx.x : blockIdx.x - Nl);
+  const float s = __ldg(scale_ptr), sp = __ldg(scale_pseudo_ptr), smix = sqrtf(sp * s);
+  const float gout = __ldg(gout_ptr);
+  const int gi = gt[i];
+  const float* self = is_img ? img : txt;
+  const float* other = is_img ? txt : img;
+  for (int c = tid; c < E; c += THREADS) a_row[c] = self[(long long)i * E + c];
+  __syncthreads();
+  const float my_lse_img = is_img ? lse_img[i] : 0.f;
+  const float my_lse_txt = is_img ? 0.f : lse_txt[i];
+  float ds = 0.f, dsp = 0.f;
+  for (int j = tid; j < Ng; j += THREADS) {
+    const int m = gi + gt[j];
+    const float c = m == 2 ? s : (m == 1 ? smix : sp);
+    const float dot = dot_row(a_row, other + (long long)j * E, E);
+    const float l = c * dot;
+    float p_img, p_txt;
+    if (is_img) { p_img = __expf(l - my_lse_img); p_txt = __expf(l - lse_txt[j]); }
+    else        { p_img = __expf(l - lse_img[j]); p_txt = __expf(l - my_lse_txt); }
+    const float d = (p_img + p_txt - ((j == i) ? 2.f : 0.f)) / (2.f * Ng);
+    w[j] = d * c;
+    // d c / d s and d c / d s_p
+    ds += d * dot * (m == 2 ? 1.f : (m == 1 ? 0.5f * smix / s : 0.f));
+    dsp += d * dot * (m == 0 ? 1.f : (m == 1 ? 0.5f * smix / sp : 0.f));
+  }
+  __syncthreads();
+  float* dst = (is_img ? d_img : d_txt) + (long long)(i - r0) * E;
+  for (int c = tid; c < E; c += THREADS) {
+    float acc = 0.f;
+    for (int j = 0; j < Ng; ++j) acc += w[j] * __ldg(other + (long long)j * E + c);
+    dst[c] = gout * grad_scale * acc;
+  }
+  if (is_img && d_scales) {
+    ds = warp_sum(ds);
+    dsp = warp_sum(dsp);
+    if ((tid & 31) == 0) { sred[0][tid >> 5] = ds; sred[1][tid >> 5] = dsp; }
+    __syncthreads();
+    if (tid == 0) {
+      float t0 = 0.f, t1 = 0.f;
+      for (int k = 0; k < THREADS / 32; ++k) { t0 += sred[0][k]; t1 += sred[1][k]; }
+      atomicAdd(d_scales, gout * scale_grad_scale * t0);
+      atomicAdd(d_scales + 1, gout * scale_grad_scale * t1);
+    }
+  }
+}
+
 }  // namespace loss
 }  // namespace lv
 
@@ -225,4 +365,29 @@ extern "C" int lv_clip_loss_bwd(const float* img, const float* txt, const float*
   LV_REQUIRE(smem <= 48 * 1024, "lv_clip_loss_bwd: Ng too large");
   loss::clip_loss_bwd_kernel<<<2 * Nl, loss::THREADS, smem, (cudaStream_t)stream>>>(img, txt, scale_ptr, lse_img, lse_txt, gout, grad_scale, scale_grad_scale, Ng, E, r0, Nl, d_img, d_txt, d_scale);
   return check_launch("lv_clip_loss_bwd");
+}
+
+extern "C" int lv_ssl_clip_loss_fwd(const float* img, const float* txt, const float* scale_ptr, const float* scale_pseudo_ptr,
+                                    const int32_t* gt, int Ng, int E, float* lse_img, float* lse_txt, float* partial,
+                                    uint32_t* counter, float* result, void* stream) {
+  LV_REQUIRE(img && txt && scale_ptr && scale_pseudo_ptr && gt && lse_img && lse_txt && partial && counter && result,
+             "lv_ssl_clip_loss_fwd: null pointer");
+  LV_REQUIRE(Ng > 0 && E > 0 && E % 4 == 0, "lv_ssl_clip_loss_fwd: bad shape Ng=%d E=%d", Ng, E);
+  const size_t smem = (size_t)(2 * E + Ng) * sizeof(float);
+  LV_REQUIRE(smem <= 48 * 1024, "lv_ssl_clip_loss_fwd: Ng=%d too large for one CTA row buffer", Ng);
+  loss::ssl_clip_loss_fwd_kernel<<<Ng, loss::THREADS, smem, (cudaStream_t)stream>>>(img, txt, scale_ptr, scale_pseudo_ptr, gt, Ng, E, lse_img, lse_txt, partial, counter, result);
+  return check_launch("lv_ssl_clip_loss_fwd");
+}
+
+extern "C" int lv_ssl_clip_loss_bwd(const float* img, const float* txt, const float* scale_ptr, const float* scale_pseudo_ptr,
+                                    const int32_t* gt, const float* lse_img, const float* lse_txt, const float* gout,
+                                    float grad_scale, float scale_grad_scale, int Ng, int E, int r0, int Nl, float* d_img,
+                                    float* d_txt, float* d_scales, void* stream) {
+  LV_REQUIRE(img && txt && scale_ptr && scale_pseudo_ptr && gt && lse_img && lse_txt && gout && d_img && d_txt,
+             "lv_ssl_clip_loss_bwd: null pointer");
+  LV_REQUIRE(Ng > 0 && E % 4 == 0 && r0 >= 0 && Nl > 0 && r0 + Nl <= Ng, "lv_ssl_clip_loss_bwd: bad shape");
+  const size_t smem = (size_t)(E + Ng) * sizeof(float);
+  LV_REQUIRE(smem <= 48 * 1024, "lv_ssl_clip_loss_bwd: Ng too large");
+  loss::ssl_clip_loss_bwd_kernel<<<2 * Nl, loss::THREADS, smem, (cudaStream_t)stream>>>(img, txt, scale_ptr, scale_pseudo_ptr, gt, lse_img, lse_txt, gout, grad_scale, scale_grad_scale, Ng, E, r0, Nl, d_img, d_txt, d_scales);
+  return check_launch("lv_ssl_clip_loss_bwd");
 }

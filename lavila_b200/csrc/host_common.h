@@ -27,6 +27,13 @@ int time_attn_small_bwd(const void* qkv, long long ld_qkv, const void* out, long
                         long long ld_dout, void* dqkv, long long ld_dqkv, float* dcls_kv, int B, int H, int T, int n,
                         cudaStream_t st);
 
+// key-tiled attention for groups of more than 208 keys (attention_big.cu), dispatched from lv_group_attn_fwd / _bwd
+int big_group_attn_fwd(const void* qkv, long long ld_qkv, void* out, long long ld_out, float* lse, int mode, int B, int H, int T,
+                       int n, cudaStream_t st);
+int big_group_attn_bwd(const void* qkv, long long ld_qkv, const void* out, long long ld_out, const float* lse, const void* dout,
+                       long long ld_dout, void* dqkv, long long ld_dqkv, float* dcls_kv, int mode, int B, int H, int T, int n,
+                       cudaStream_t st);
+
 }  // namespace lv
 
 #define LV_REQUIRE(cond, ...)                                  \

@@ -68,3 +68,15 @@ def gather_embeddings(image_features, text_features, world_size):
     dist.all_gather(buf, local)
     allb = torch.stack(buf, 0).view(world_size * B, 2 * E)
     return allb[:, :E].contiguous(), allb[:, E:].contiguous()
+
+
+def gather_embeddings_gt(image_features, text_features, gt_indicators, world_size):
+    """SSLCLIPLoss (loss.py:155-157 issues three gather_from_all): ONE all_gather of [image | text | gt] ([B, 2E+1]).
+    Returns (all_image [W*B, E], all_text [W*B, E], all_gt [W*B] float) in rank order, without autograd history."""
+    B, E = image_features.shape
+    gt = gt_indicators.detach().reshape(-1, 1).to(device=image_features.device, dtype=image_features.dtype)
+    local = torch.cat((image_features.detach(), text_features.detach(), gt), dim=1).contiguous()
+    buf = [torch.empty_like(local) for _ in range(world_size)]
+    dist.all_gather(buf, local)
+    allb = torch.stack(buf, 0).view(world_size * B, 2 * E + 1)
+    return allb[:, :E].contiguous(), allb[:, E:2 * E].contiguous(), allb[:, 2 * E].contiguous()

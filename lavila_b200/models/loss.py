@@ -1,4 +1,4 @@
-"""CLIPLoss -- mirror of lavila/models/loss.py:18-118 on the fused B200 kernels.
+"""CLIPLoss / SSLCLIPLoss -- mirror of lavila/models/loss.py:18-217 on the fused B200 kernels.
 
 forward(outputs) takes the dict returned by CLIP.forward and returns {'loss', 'clip_loss', 'clip_acc'} (0-dim tensors).
 Multi-GPU (world_size > 1): one all-gather of [image | text] embeddings over NCCL/NVLink, then every rank evaluates the
@@ -6,11 +6,12 @@ global N x N loss redundantly (exactly what the reference does, loss.py:76-79) i
 collective: all ranks hold the same global loss, so the reference's all_reduce(SUM) of identical per-rank embedding
 gradients (distributed_utils.py:64-67) equals a multiplication by world_size, applied as `grad_scale`.
 """
+import numpy as np
 import torch
 import torch.nn as nn
 
 from .. import ops
-from .distributed_utils import gather_embeddings
+from .distributed_utils import gather_embeddings, gather_embeddings_gt
 
 F32 = torch.float32
 
@@ -104,3 +105,84 @@ class CLIPLoss(nn.Module):
         loss, acc = _ClipLossFn.apply(image_features, text_features, logit_scale, self.rank, self.world_size,
                                       grad_scale, self._state)
         return {'loss': loss, 'clip_loss': loss, 'clip_acc': acc}
+
+
+class _SSLClipLossFn(torch.autograd.Function):
+    """SSLCLIPLoss core (loss.py:148-213) on the gathered batch: one forward kernel (logits with the per-pair scale,
+    both log-sum-exps, arg-max, the three accuracies) and one backward kernel; as for CLIPLoss, no backward collective."""
+
+    @staticmethod
+    def forward(ctx, image, text, logit_scale, scale_pseudo, gt, rank, world_size, grad_scale, state):
+        image = image.contiguous().float()
+        text = text.contiguous().float()
+        B, E = image.shape
+        dev = image.device
+        gt_f = gt.detach().reshape(-1).to(device=dev, dtype=F32)
+        if world_size > 1:
+            all_i, all_t, all_g = gather_embeddings_gt(image, text, gt_f, world_size)
+        else:
+            all_i, all_t, all_g = image, text, gt_f
+        gt_i = all_g.round().to(torch.int32).contiguous()
+        Ng = all_i.shape[0]
+        scale = logit_scale.detach().reshape(1).contiguous().float()
+        scale_p = scale_pseudo.detach().reshape(1).contiguous().float()
+        lse_i = torch.empty(Ng, device=dev, dtype=F32)
+        lse_t = torch.empty(Ng, device=dev, dtype=F32)
+        partial = torch.empty(2 * Ng, device=dev, dtype=F32)
+        result = torch.empty(6, device=dev, dtype=F32)
+        if state.get("counter") is None or state["counter"].device != dev:
+            state["counter"] = torch.zeros(1, device=dev, dtype=torch.int32)
+        ops.ssl_clip_loss_fwd(all_i, all_t, scale, scale_p, gt_i, Ng, E, lse_i, lse_t, partial, state["counter"], result)
+        ctx.saved = (all_i, all_t, scale, scale_p, gt_i, lse_i, lse_t)
+        ctx.meta = (B, E, Ng, rank, world_size, grad_scale)
+        stats = result[1:]
+        ctx.mark_non_differentiable(stats)
+        return result[0], stats
+
+    @staticmethod
+    def backward(ctx, gloss, gstats):
+        all_i, all_t, scale, scale_p, gt_i, lse_i, lse_t = ctx.saved
+        ctx.saved = None
+        B, E, Ng, rank, world_size, grad_scale = ctx.meta
+        dev = all_i.device
+        d_i = torch.empty(Ng, E, device=dev, dtype=F32)
+        d_t = torch.empty(Ng, E, device=dev, dtype=F32)
+        d_s = torch.zeros(2, device=dev, dtype=F32)
+        g = gloss.reshape(1).contiguous().float()
+        ops.ssl_clip_loss_bwd(all_i, all_t, scale, scale_p, gt_i, lse_i, lse_t, g, grad_scale, 1.0, Ng, E, 0, Ng, d_i, d_t, d_s)
+        sl = slice(rank * B, (rank + 1) * B)
+        return d_i[sl], d_t[sl], d_s[0].reshape(()), d_s[1].reshape(()), None, None, None, None, None
+
+
+class SSLCLIPLoss(nn.Module):
+    """loss.py:121-217: dual-temperature contrastive loss over human (gt_indicators = 1) and pseudo-narrated (0) pairs,
+    selected by main_pretrain.py:189-197 when --metadata-aux is given (the LaViLa recipe, docs/PRETRAIN.md:109-122)."""
+
+    def __init__(self, use_vissl=False, local_loss=False, gather_with_grad=False, cache_labels=False, rank=0, world_size=1,
+                 scale_init=0.08, freeze_scale=False):
+        super().__init__()
+        self.use_vissl = use_vissl
+        self.local_loss = local_loss
+        self.gather_with_grad = gather_with_grad
+        self.cache_labels = cache_labels
+        self.rank = rank
+        self.world_size = world_size
+        self.logit_scale_pseudo = nn.Parameter(torch.ones([]) * np.log(1 / scale_init))
+        if freeze_scale:
+            self.logit_scale_pseudo.requires_grad = False
+        self.prev_num_logits = 0
+        self.labels = {}
+        self._state = {}
+
+    def forward(self, outputs, gt_indicators):
+        if self.world_size > 1 and not self.use_vissl:
+            raise NotImplementedError   # loss.py:167-168
+        logit_scale_pseudo = self.logit_scale_pseudo.exp()
+        grad_scale = float(self.world_size) if self.world_size > 1 else 1.0   # GatherLayer semantics (use_vissl)
+        loss, st = _SSLClipLossFn.apply(outputs['image_embed'], outputs['text_embed'], outputs['logit_scale'],
+                                        logit_scale_pseudo, gt_indicators, self.rank, self.world_size, grad_scale,
+                                        self._state)
+        # the reference returns the two counts as CPU LongTensors of shape [1] (loss.py:210); that forces one D2H read
+        counts = st[3:5].round().to(torch.int64).cpu()
+        return {'loss': loss, 'clip_loss': loss, 'num_gt': counts[0:1], 'num_pseudo': counts[1:2],
+                'clip_acc': st[0], 'clip_acc_gt': st[1], 'clip_acc_pseudo': st[2]}

@@ -10,6 +10,7 @@ import torch.nn as nn
 
 from .. import engine as E
 from . import loss as loss_mod
+from . import loss  # noqa: F401  main_pretrain.py:189 reaches SSLCLIPLoss as `models.loss.SSLCLIPLoss`
 from .openai_model import QuickGELU, Transformer
 from .timesformer import SpaceTimeTransformer
 
@@ -92,7 +93,7 @@ def get_loss(model, args, tokenizer=None):
 
 
 def get_metric_names(model):
-    """models.py:307-313."""
+    """models.py:307-313 (the SSLCLIPLoss run adds clip_acc_gt / clip_acc_pseudo itself, main_pretrain.py:235-236)."""
     if model.startswith('CLIP'):
         return ['loss', 'clip_loss', 'clip_acc']
     raise NotImplementedError
@@ -189,7 +190,35 @@ def VCLM_OPENAI_TIMESFORMER_BASE_GPT2(gated_xattn=False, random_init_gpt2=False,
 def VCLM_OPENAI_TIMESFORMER_BASE_GPT2_XL(gated_xattn=False, random_init_gpt2=False, freeze_lm_vclm=False,
                                          freeze_visual_vclm=False, freeze_visual_vclm_temporal=False, num_frames=4,
                                          timesformer_gated_xattn=False, checkpoint=None, **kwargs):
-    """TSF-B/16 + GPT-2 XL (1600/48/25), cross-attention every 2nd layer, 25 pooling heads (the decoder of
-    models.py:1012-1072; the TSF-L/14 video encoder of that factory needs key-tiled space attention -- next)."""
+    """models.py:951-1009: TSF-B/16 + GPT-2 XL (1600/48/25), cross-attention every 2nd layer, 25 pooling heads."""
     return _vclm({}, 768, dict(n_embd=1600, n_layer=48, n_head=25), 2, 25, num_frames, gated_xattn, timesformer_gated_xattn,
                  freeze_lm_vclm, freeze_visual_vclm, freeze_visual_vclm_temporal, checkpoint, kwargs)
+
+
+_TSF_L = dict(img_size=224, patch_size=14, embed_dim=1024, depth=24, num_heads=16)
+_TSF_L_336 = dict(img_size=336, patch_size=14, embed_dim=1024, depth=24, num_heads=16)
+
+
+def VCLM_OPENAI_TIMESFORMER_LARGE_GPT2_XL(gated_xattn=False, random_init_gpt2=False, freeze_lm_vclm=False,
+                                          freeze_visual_vclm=False, freeze_visual_vclm_temporal=False, num_frames=4,
+                                          timesformer_gated_xattn=False, checkpoint=None, **kwargs):
+    """models.py:1012-1072 (the NARRATOR of BASELINE config 4): TSF-L/14 224px (256 patches per frame: key-tiled space
+    attention, csrc/attention_big.cu) + GPT-2 XL, cross-attention every 2nd layer, 25 pooling heads."""
+    return _vclm(dict(_TSF_L), 1024, dict(n_embd=1600, n_layer=48, n_head=25), 2, 25, num_frames, gated_xattn,
+                 timesformer_gated_xattn, freeze_lm_vclm, freeze_visual_vclm, freeze_visual_vclm_temporal, checkpoint, kwargs)
+
+
+def VCLM_OPENAI_TIMESFORMER_LARGE_GPT2(gated_xattn=False, random_init_gpt2=False, freeze_lm_vclm=False,
+                                       freeze_visual_vclm=False, freeze_visual_vclm_temporal=False, num_frames=4,
+                                       timesformer_gated_xattn=False, checkpoint=None, **kwargs):
+    """models.py:1075-1135: TSF-L/14 224px + GPT-2 (768/12/12), cross-attention in every layer, 12 pooling heads."""
+    return _vclm(dict(_TSF_L), 1024, dict(n_embd=768, n_layer=12, n_head=12), 1, 12, num_frames, gated_xattn,
+                 timesformer_gated_xattn, freeze_lm_vclm, freeze_visual_vclm, freeze_visual_vclm_temporal, checkpoint, kwargs)
+
+
+def VCLM_OPENAI_TIMESFORMER_LARGE_336PX_GPT2_XL(gated_xattn=False, random_init_gpt2=False, freeze_lm_vclm=False,
+                                                freeze_visual_vclm=False, freeze_visual_vclm_temporal=False, num_frames=4,
+                                                timesformer_gated_xattn=False, checkpoint=None, **kwargs):
+    """models.py:1138-1198: TSF-L/14 336px (576 patches per frame) + GPT-2 XL, cross-attention every 3rd layer."""
+    return _vclm(dict(_TSF_L_336), 1024, dict(n_embd=1600, n_layer=48, n_head=25), 3, 25, num_frames, gated_xattn,
+                 timesformer_gated_xattn, freeze_lm_vclm, freeze_visual_vclm, freeze_visual_vclm_temporal, checkpoint, kwargs)

@@ -227,3 +227,19 @@ def clip_loss_bwd(img, txt, scale, lse_img, lse_txt, gout, grad_scale, scale_gra
                                   lse_txt.data_ptr(), gout.data_ptr(), float(grad_scale), float(scale_grad_scale), Ng, E,
                                   r0, Nl, d_img.data_ptr(), d_txt.data_ptr(), _p(d_scale), _stream())
     L.check(rc, "lv_clip_loss_bwd")
+
+
+def ssl_clip_loss_fwd(img, txt, scale, scale_pseudo, gt, Ng, E, lse_img, lse_txt, partial, counter, result):
+    rc = L.lib().lv_ssl_clip_loss_fwd(img.data_ptr(), txt.data_ptr(), scale.data_ptr(), scale_pseudo.data_ptr(),
+                                      gt.data_ptr(), Ng, E, lse_img.data_ptr(), lse_txt.data_ptr(), partial.data_ptr(),
+                                      counter.data_ptr(), result.data_ptr(), _stream())
+    L.check(rc, "lv_ssl_clip_loss_fwd")
+
+
+def ssl_clip_loss_bwd(img, txt, scale, scale_pseudo, gt, lse_img, lse_txt, gout, grad_scale, scale_grad_scale, Ng, E, r0,
+                      Nl, d_img, d_txt, d_scales):
+    rc = L.lib().lv_ssl_clip_loss_bwd(img.data_ptr(), txt.data_ptr(), scale.data_ptr(), scale_pseudo.data_ptr(),
+                                      gt.data_ptr(), lse_img.data_ptr(), lse_txt.data_ptr(), gout.data_ptr(),
+                                      float(grad_scale), float(scale_grad_scale), Ng, E, r0, Nl, d_img.data_ptr(),
+                                      d_txt.data_ptr(), _p(d_scales), _stream())
+    L.check(rc, "lv_ssl_clip_loss_bwd")

@@ -178,6 +178,33 @@ def clip_loss_multi_rank(image_per_rank, text_per_rank, logit_scale):
     return out
 
 
+def ssl_clip_loss(all_image, all_text, logit_scale, logit_scale_pseudo, gt_indicators):
+    """lavila/models/loss.py:148-213 (SSLCLIPLoss.forward) on the (already gathered) global batch.
+    `logit_scale` is the model output (already exp'ed, models.py:173); `logit_scale_pseudo` is the loss module's
+    log-parameter (loss.py:140, exp'ed at :152); gt_indicators[i] = 1 for a human narration, 0 for a pseudo one.
+    Pair scale: both pseudo -> s_p, mixed -> sqrt(s_p * s), both human -> s  (loss.py:160-164 / :172-176)."""
+    sp = logit_scale_pseudo.exp()
+    num = gt_indicators.shape[0]
+    mask = gt_indicators.repeat(num, 1) + gt_indicators.repeat(num, 1).t()
+    mat = torch.ones((num, num), device=all_image.device) * sp
+    mat = torch.where(mask == 1, torch.sqrt(sp * logit_scale), mat)
+    mat = torch.where(mask == 2, logit_scale * torch.ones_like(mat), mat)
+    logits_i = mat * (all_image @ all_text.t())
+    logits_t = logits_i.t()                                    # mat is symmetric: equals mat * (T @ I^T) of :178
+    labels = torch.arange(num, device=logits_i.device)
+    loss = (F.cross_entropy(logits_i, labels) + F.cross_entropy(logits_t, labels)) / 2
+    with torch.no_grad():
+        pred = logits_i.argmax(dim=-1)
+        acc = 100 * pred.eq(labels).sum() / num
+        is_gt = gt_indicators == 1
+        is_ps = gt_indicators == 0
+        num_gt, num_pseudo = int(is_gt.sum()), int(is_ps.sum())
+        acc_gt = 100 * pred[is_gt].eq(labels[is_gt]).sum() / num_gt
+        acc_pseudo = 100 * pred[is_ps].eq(labels[is_ps]).sum() / num_pseudo
+    return {"loss": loss, "clip_loss": loss, "num_gt": torch.tensor([num_gt]), "num_pseudo": torch.tensor([num_pseudo]),
+            "clip_acc": acc, "clip_acc_gt": acc_gt, "clip_acc_pseudo": acc_pseudo}
+
+
 # ----------------------------------------------------------------------------------------------- configs / inputs
 def tsf_base_config(num_frames=16, img_size=224):
     """CLIP_OPENAI_TIMESFORMER_BASE -- lavila/models/models.py:316-361."""

@@ -27,6 +27,11 @@ def _worker(rank, world, port, ret):
     (gathered * torch.arange(world * B * E, dtype=torch.float32).view(world * B, E)).sum().backward()
     expect = world * torch.arange(world * B * E, dtype=torch.float32).view(world * B, E)[rank * B:(rank + 1) * B]
     ok = ok and torch.allclose(x.grad, expect)
+    # SSLCLIPLoss: [image | text | gt] in one collective == three reference gathers (loss.py:155-157)
+    from lavila_b200.models.distributed_utils import gather_embeddings_gt
+    gt = torch.tensor([1., 0., 1.]) if rank == 0 else torch.tensor([0., 0., 1.])
+    a_i, a_t, a_g = gather_embeddings_gt(img, txt, gt, world)
+    ok = ok and torch.equal(a_i, ref_i) and torch.equal(a_t, ref_t) and torch.equal(a_g, gather_from_all(gt))
     ret[rank] = bool(ok)
     dist.destroy_process_group()
 

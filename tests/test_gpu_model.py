@@ -128,3 +128,33 @@ def test_cls_only_tail_equals_full_last_block():
             continue
         r = rel_l2(res[True][1][n], g)
         assert r < 3e-2, "%s: %.3e" % (n, r)
+
+
+def test_clip_tsf_l14_geometry_vs_oracle():
+    """TSF-L/14 geometry (224 px / patch 14 -> 256 patches per frame, 257 keys per space group: the key-tiled attention
+    of csrc/attention_big.cu; im2col with K = 588 padded to 592) at toy width: full CLIP forward + CLIPLoss + backward
+    against the fp32 oracle."""
+    from lavila_b200.models.loss import CLIPLoss
+    cfg = dict(img_size=224, patch_size=14, embed_dim=128, depth=2, num_heads=2, num_frames=2, ln_pre=True,
+               text_width=128, text_heads=2, text_layers=1, context_length=16, vocab_size=512, project_dim=64)
+    params = O.init_params(cfg, seed=5)
+    model = build_clip(cfg, params)
+    model.visual.cls_only_tail = False          # exercise the full last block (space attention fwd + bwd) too
+    frames, text = O.synthetic_batch(cfg, 3, seed=77)
+    out = model(frames.to(DEV), text.to(DEV), norm_embed=True)
+    ld = CLIPLoss()(out)
+    ld["loss"].backward()
+    pr = {k: v.to(DEV).requires_grad_(True) for k, v in params.items()}
+    ref = O.clip_forward(frames.to(DEV), text.to(DEV), pr, cfg, norm_embed=True)
+    rl = O.clip_loss(ref["image_embed"], ref["text_embed"], ref["logit_scale"])
+    rl["loss"].backward()
+    assert_close_bf16(out["image_embed"], ref["image_embed"], "image_embed (n = 256)")
+    assert abs(float(ld["loss"]) - float(rl["loss"])) < 3e-2
+    named = dict(model.named_parameters())
+    for name in ["visual.blocks.0.attn.qkv.weight", "visual.blocks.1.attn.qkv.weight", "visual.blocks.0.timeattn.qkv.weight",
+                 "visual.patch_embed.proj.weight", "visual.cls_token", "visual.pos_embed", "visual.temporal_embed"]:
+        g, want = named[name].grad, pr[name].grad
+        if float(want.norm()) < 1e-7:
+            continue
+        r, cs = rel_l2(g, want), cosine(g, want)
+        assert cs > 0.99 and r < 6e-2, "%s: rel_l2 %.3e cosine %.5f" % (name, r, cs)

@@ -130,9 +130,63 @@ def _attn_case(mode, B, H, T, n, seed):
 
 @pytest.mark.parametrize("mode,B,H,T,n", [("space", 2, 2, 4, 4), ("time", 2, 2, 4, 4), ("space", 1, 3, 2, 196),
                                           ("time", 1, 3, 16, 9), ("space", 2, 12, 16, 196), ("time", 2, 12, 16, 196),
-                                          ("time", 2, 16, 8, 5), ("time", 3, 12, 16, 49)])
+                                          ("time", 2, 16, 8, 5), ("time", 3, 12, 16, 49),
+                                          # TSF-L/14 geometries: 256 / 576 patches per frame (key-tiled kernels), 32 frames
+                                          ("space", 1, 2, 2, 256), ("space", 2, 3, 3, 576), ("space", 1, 2, 2, 209),
+                                          ("time", 1, 2, 32, 5), ("time", 1, 1, 250, 2)])
 def test_var_attention(mode, B, H, T, n):
     _attn_case(mode, B, H, T, n, seed=3)
+
+
+@pytest.mark.parametrize("mode,B,H,T,n", [(0, 1, 1, 1, 320), (0, 2, 2, 3, 257), (0, 1, 16, 2, 576), (1, 1, 2, 300, 3)])
+def test_tiled_group_attention_direct(mode, B, H, T, n):
+    """lv_group_attn_fwd / _bwd on groups of more than 208 keys (attention_big.cu) against fp32 torch math on the same
+    bf16 qkv: out, lse, dq / dk / dv of the patch rows and the CLS key/value gradient accumulator."""
+    ops, _ = _ops()
+    torch.manual_seed(11)
+    D, N = 64 * H, 1 + T * n
+    qkv = (torch.randn(B * N, 3 * D, device=DEV) * 1.5).to(torch.bfloat16)
+    dout = torch.randn(B * N, D, device=DEV).to(torch.bfloat16)
+    out = torch.zeros(B * N, D, device=DEV, dtype=torch.bfloat16)
+    lse = torch.zeros(B * N, H, device=DEV)
+    ops.group_attn_fwd(qkv, out, lse, mode, B, H, T=T, n=n)
+    # reference: [B, H, groups, Lq, 64] queries; keys = group rows + CLS
+    x = qkv.float().view(B, N, 3, H, 64).requires_grad_(True)
+    q, k, v = x[:, :, 0], x[:, :, 1], x[:, :, 2]                      # [B, N, H, 64]
+
+    def grp(t):   # patch rows -> [B, H, G, Lq, 64]
+        t = t[:, 1:].reshape(B, T, n, H, 64)
+        return t.permute(0, 3, 1, 2, 4) if mode == 0 else t.permute(0, 3, 2, 1, 4)
+    G = T if mode == 0 else n
+    qg, kg, vg = grp(q), grp(k), grp(v)
+    kc = k[:, :1].permute(0, 2, 1, 3)[:, :, None].expand(B, H, G, 1, 64)
+    vc = v[:, :1].permute(0, 2, 1, 3)[:, :, None].expand(B, H, G, 1, 64)
+    ka, va = torch.cat([kg, kc], 3), torch.cat([vg, vc], 3)
+    sc = torch.einsum("bhgqd,bhgkd->bhgqk", qg, ka) * 0.125
+    ref_lse = torch.logsumexp(sc, -1)
+    ref_o = torch.einsum("bhgqk,bhgkd->bhgqd", sc.softmax(-1), va)
+
+    def ungrp(t):  # [B, H, G, Lq, 64] -> [B, T*n, H, 64]
+        t = t.permute(0, 2, 3, 1, 4) if mode == 0 else t.permute(0, 3, 2, 1, 4)
+        return t.reshape(B, T * n, H, 64)
+    got_o = out.view(B, N, H, 64)[:, 1:]
+    assert_close_bf16(got_o, ungrp(ref_o), "tiled attention out")
+    lg = lse.view(B, N, H)[:, 1:]
+    lr = (ref_lse.permute(0, 2, 3, 1) if mode == 0 else ref_lse.permute(0, 3, 2, 1)).reshape(B, T * n, H)
+    lse_err = float((lg - lr.detach()).abs().max())
+    assert lse_err < 2e-2, "lse max abs diff %.3e" % lse_err
+    # backward: feed the kernel's own (bf16) forward output, as the engine does
+    do = dout.float().view(B, N, H, 64)[:, 1:]
+    (ungrp(ref_o) * do).sum().backward()
+    dqkv = torch.zeros(B * N, 3 * D, device=DEV, dtype=torch.bfloat16)
+    dcls = torch.zeros(B, H, 2, 64, device=DEV)
+    ops.group_attn_bwd(qkv, out, lse, dout, dqkv, dcls, 0, mode, B, H, T=T, n=n)
+    gd = dqkv.float().view(B, N, 3, H, 64)
+    for i, nm in enumerate(["dq", "dk", "dv"]):
+        assert_close_bf16(gd[:, 1:, i], x.grad[:, 1:, i], "tiled attention " + nm, rel=3e-2)
+    assert_close_bf16(dcls[:, :, 0], x.grad[:, 0, 1], "tiled attention d cls key", rel=3e-2)
+    assert_close_bf16(dcls[:, :, 1], x.grad[:, 0, 2], "tiled attention d cls value", rel=3e-2)
+    assert float(gd[:, 0].abs().max()) == 0.0, "the group kernels must not touch the CLS row of dqkv"
 
 
 def test_mlp():
@@ -193,3 +247,60 @@ def test_clip_loss_single_rank():
     assert float(out["clip_acc"]) == float(ref["clip_acc"])
     assert rel_l2(img.grad, ir.grad) < 1e-4 and rel_l2(txt.grad, tr.grad) < 1e-4
     assert abs(float(ls.grad) - float(lr.grad)) < 1e-4 * max(1.0, abs(float(lr.grad)))
+
+
+@pytest.mark.parametrize("idx", [0, 1, 2, 3])
+def test_ssl_clip_loss_matches_reference_golden(idx):
+    """SSLCLIPLoss (lavila/models/loss.py:121-217) through the fused kernels against golden vectors of the UNMODIFIED
+    reference (tests/golden/make_golden_ssl.py): loss, the three accuracies (NaN for an empty class, as the reference),
+    the counts (bit exact) and the gradients w.r.t. embeddings, logit_scale and logit_scale_pseudo.  fp32 -> 1e-4."""
+    import os
+    from lavila_b200.models.loss import SSLCLIPLoss
+    G = torch.load(os.path.join(os.path.dirname(__file__), "golden", "ssl_loss_small.pt"), weights_only=False)
+    c = G["world1"][idx]
+    crit = SSLCLIPLoss(scale_init=G["scale_init"]).to(DEV)
+    img = c["image"].to(DEV).requires_grad_(True)
+    txt = c["text"].to(DEV).requires_grad_(True)
+    s = torch.tensor(G["scale"], device=DEV, requires_grad=True)
+    out = crit({"image_embed": img, "text_embed": txt, "logit_scale": s}, c["gt"].to(DEV))
+    gi, gt, gs, gp = torch.autograd.grad(out["loss"], (img, txt, s, crit.logit_scale_pseudo))
+    assert abs(float(out["loss"]) - float(c["loss"])) < 1e-4
+    for k in ("clip_acc", "clip_acc_gt", "clip_acc_pseudo"):
+        a, b = float(out[k]), float(c[k])
+        assert (a != a and b != b) or abs(a - b) < 1e-3, (k, a, b)
+    assert int(out["num_gt"]) == int(c["num_gt"]) and int(out["num_pseudo"]) == int(c["num_pseudo"])
+    assert out["num_gt"].shape == c["num_gt"].shape and out["num_gt"].dtype == c["num_gt"].dtype
+    assert rel_l2(gi, c["grad_image"]) < 1e-4 and rel_l2(gt, c["grad_text"]) < 1e-4
+    assert abs(float(gs) - float(c["grad_scale"])) < 1e-5 + 1e-4 * abs(float(c["grad_scale"]))
+    assert abs(float(gp) - float(c["grad_scale_pseudo"])) < 1e-5 + 1e-4 * abs(float(c["grad_scale_pseudo"]))
+
+
+def test_ssl_clip_loss_two_rank_rows():
+    """The 2-rank golden (reference SSLCLIPLoss(use_vissl) over gloo): the kernels evaluated on the gathered batch give
+    every rank's loss, and the local-row gradient slices times W equal the reference's GatherLayer gradients."""
+    import os
+    ops, _ = _ops()
+    G = torch.load(os.path.join(os.path.dirname(__file__), "golden", "ssl_loss_small.pt"), weights_only=False)
+    r = G["world2"]
+    W, B = len(r), r[0]["image"].shape[0]
+    img = torch.cat([x["image"] for x in r]).to(DEV).contiguous()
+    txt = torch.cat([x["text"] for x in r]).to(DEV).contiguous()
+    gt = torch.cat([x["gt"] for x in r]).to(DEV).to(torch.int32).contiguous()
+    Ng, E = img.shape
+    s = torch.tensor([G["scale"]], device=DEV)
+    sp = torch.tensor([1.0 / G["scale_init"]], device=DEV)
+    lse_i, lse_t = torch.empty(Ng, device=DEV), torch.empty(Ng, device=DEV)
+    partial, result = torch.empty(2 * Ng, device=DEV), torch.empty(6, device=DEV)
+    counter = torch.zeros(1, device=DEV, dtype=torch.int32)
+    ops.ssl_clip_loss_fwd(img, txt, s, sp, gt, Ng, E, lse_i, lse_t, partial, counter, result)
+    g = torch.ones(1, device=DEV)
+    for k in range(W):
+        assert abs(float(result[0]) - float(r[k]["loss"])) < 1e-4
+        d_i, d_t, d_s = torch.empty(B, E, device=DEV), torch.empty(B, E, device=DEV), torch.zeros(2, device=DEV)
+        ops.ssl_clip_loss_bwd(img, txt, s, sp, gt, lse_i, lse_t, g, float(W), 1.0, Ng, E, k * B, B, d_i, d_t, d_s)
+        assert rel_l2(d_i, r[k]["grad_image"]) < 1e-4 and rel_l2(d_t, r[k]["grad_text"]) < 1e-4
+    d_i, d_t, d_s = torch.empty(Ng, E, device=DEV), torch.empty(Ng, E, device=DEV), torch.zeros(2, device=DEV)
+    ops.ssl_clip_loss_bwd(img, txt, s, sp, gt, lse_i, lse_t, g, float(W), 1.0, Ng, E, 0, Ng, d_i, d_t, d_s)
+    assert abs(float(d_s[0]) - float(r[0]["grad_scale"])) < 1e-5 + 1e-4 * abs(float(r[0]["grad_scale"]))
+    # the reference's gradient is w.r.t. the log-parameter: d/d log(s_p) = s_p * d/d s_p
+    assert abs(float(d_s[1] * sp[0]) - float(r[0]["grad_scale_pseudo"])) < 1e-5 + 1e-4 * abs(float(r[0]["grad_scale_pseudo"]))

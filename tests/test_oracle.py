@@ -79,3 +79,52 @@ def test_known_answers():
     out = O.clip_loss(e, e, torch.tensor(100.0))
     assert float(out["clip_acc"]) == 100.0
     assert float(out["loss"]) < 0.05
+
+
+# ----------------------------------------------------------------------------------------------- SSLCLIPLoss
+SSL = torch.load(os.path.join(os.path.dirname(__file__), "golden", "ssl_loss_small.pt"), weights_only=False)
+
+
+def _ssl_oracle(img, txt, gt, scale_init):
+    import math
+    img, txt = img.clone().requires_grad_(True), txt.clone().requires_grad_(True)
+    s = torch.tensor(SSL["scale"], requires_grad=True)
+    lp = torch.tensor(math.log(1 / scale_init), requires_grad=True)
+    out = O.ssl_clip_loss(img, txt, s, lp, gt)
+    return out, torch.autograd.grad(out["loss"], (img, txt, s, lp))
+
+
+def _same(a, b):
+    a, b = torch.as_tensor(a).float().reshape(-1), torch.as_tensor(b).float().reshape(-1)
+    if torch.isnan(b).any():
+        return bool(torch.isnan(a).all())
+    return bool(torch.allclose(a, b, rtol=1e-5, atol=1e-6))
+
+
+@pytest.mark.parametrize("idx", [0, 1, 2, 3])
+def test_ssl_clip_loss_matches_reference_golden(idx):
+    c = SSL["world1"][idx]
+    out, (gi, gt, gs, gp) = _ssl_oracle(c["image"], c["text"], c["gt"], SSL["scale_init"])
+    for k in ("loss", "clip_acc", "clip_acc_gt", "clip_acc_pseudo", "num_gt", "num_pseudo"):
+        assert _same(out[k], c[k]), (k, out[k], c[k])
+    torch.testing.assert_close(gi, c["grad_image"], rtol=1e-4, atol=1e-7)
+    torch.testing.assert_close(gt, c["grad_text"], rtol=1e-4, atol=1e-7)
+    torch.testing.assert_close(gs, c["grad_scale"], rtol=1e-4, atol=1e-7)
+    torch.testing.assert_close(gp, c["grad_scale_pseudo"], rtol=1e-4, atol=1e-7)
+
+
+def test_ssl_clip_loss_multirank_semantics():
+    """2-rank SSLCLIPLoss(use_vissl): every rank's loss == the single-process loss on the concatenated batch; the
+    local-embedding gradient is W x the single-process one (GatherLayer), the scale gradients are 1 x."""
+    r = SSL["world2"]
+    W = len(r)
+    img, txt, gt = torch.cat([x["image"] for x in r]), torch.cat([x["text"] for x in r]), torch.cat([x["gt"] for x in r])
+    out, (gi, gtx, gs, gp) = _ssl_oracle(img, txt, gt, SSL["scale_init"])
+    B = r[0]["image"].shape[0]
+    for k in range(W):
+        assert _same(out["loss"], r[k]["loss"]) and _same(out["clip_acc"], r[k]["clip_acc"])
+        assert _same(out["clip_acc_gt"], r[k]["clip_acc_gt"]) and _same(out["clip_acc_pseudo"], r[k]["clip_acc_pseudo"])
+        torch.testing.assert_close(W * gi[k * B:(k + 1) * B], r[k]["grad_image"], rtol=1e-4, atol=1e-7)
+        torch.testing.assert_close(W * gtx[k * B:(k + 1) * B], r[k]["grad_text"], rtol=1e-4, atol=1e-7)
+        torch.testing.assert_close(gs, r[k]["grad_scale"], rtol=1e-4, atol=1e-7)
+        torch.testing.assert_close(gp, r[k]["grad_scale_pseudo"], rtol=1e-4, atol=1e-7)

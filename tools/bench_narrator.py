@@ -23,6 +23,8 @@ def main():
     ap.add_argument("--max-len", type=int, default=77)
     ap.add_argument("--impl", default="ours", choices=["ours", "eager"])
     ap.add_argument("--decoder", default="xl", choices=["xl", "base"])
+    ap.add_argument("--encoder", default="base", choices=["base", "large"],
+                    help="large = TSF-L/14 224px: VCLM_OPENAI_TIMESFORMER_LARGE_GPT2_XL, the model BASELINE config 4 names")
     a = ap.parse_args()
     dev = torch.device("cuda", 0)
     torch.manual_seed(0)
@@ -30,7 +32,9 @@ def main():
     frames = torch.randn(a.batch, 3, a.frames, 224, 224, device=dev)
     if a.impl == "ours":
         from lavila_b200.models import models as M
-        f = M.VCLM_OPENAI_TIMESFORMER_BASE_GPT2_XL if a.decoder == "xl" else M.VCLM_OPENAI_TIMESFORMER_BASE_GPT2
+        f = {("base", "xl"): M.VCLM_OPENAI_TIMESFORMER_BASE_GPT2_XL, ("base", "base"): M.VCLM_OPENAI_TIMESFORMER_BASE_GPT2,
+             ("large", "xl"): M.VCLM_OPENAI_TIMESFORMER_LARGE_GPT2_XL, ("large", "base"): M.VCLM_OPENAI_TIMESFORMER_LARGE_GPT2}[
+            (a.encoder, a.decoder)]
         model = f(gated_xattn=True, num_frames=a.frames).to(dev).eval()
         with torch.no_grad():
             for n, p in model.named_parameters():
@@ -46,7 +50,9 @@ def main():
     else:
         from oracle import narrator as ON
         H, Ld, nh, freq = (1600, 48, 25, 2) if a.decoder == "xl" else (768, 12, 12, 1)
-        cfg = dict(visual=dict(img_size=224, patch_size=16, embed_dim=768, depth=12, num_heads=12, num_frames=a.frames, ln_pre=True),
+        vis = dict(img_size=224, patch_size=16, embed_dim=768, depth=12, num_heads=12) if a.encoder == "base" else \
+            dict(img_size=224, patch_size=14, embed_dim=1024, depth=24, num_heads=16)
+        cfg = dict(visual=dict(num_frames=a.frames, ln_pre=True, **vis),
                    n_embd=H, n_head=nh, n_layer=Ld, cross_attn_freq=freq, vocab_size=50257, n_positions=1024,
                    num_img_queries=256, pool_heads=nh)
         p = {k: v.to(dev) for k, v in ON.init_narrator_params(cfg, seed=0).items()}
@@ -68,7 +74,7 @@ def main():
     ids, _ = run()
     torch.cuda.synchronize()
     dt = time.time() - t0
-    print(json.dumps({"impl": a.impl, "decoder": a.decoder, "batch": a.batch, "returns": a.returns, "frames": a.frames,
+    print(json.dumps({"impl": a.impl, "encoder": a.encoder, "decoder": a.decoder, "batch": a.batch, "returns": a.returns, "frames": a.frames,
                       "tokens": int(ids.shape[1]), "seconds": round(dt, 3), "clips_per_s": round(a.batch / dt, 3),
                       "sequences_per_s": round(a.batch * a.returns / dt, 3),
                       "max_mem_gb": round(torch.cuda.max_memory_allocated() / 2 ** 30, 1)}))
