@@ -37,6 +37,11 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "eager"])
     ap.add_argument("--batch", type=int, default=64, help="clips per GPU (BASELINE config: 64)")
     ap.add_argument("--frames", type=int, default=16)
+    ap.add_argument("--model", default="base", choices=["base", "large", "large336"],
+                    help="base = CLIP_OPENAI_TIMESFORMER_BASE (the BASELINE metric); large / large336 = the TSF-L/14 factories "
+                         "(BASELINE config 5 is large336 at --frames 32), ours arm only")
+    ap.add_argument("--use-checkpoint", action="store_true",
+                    help="model(..., use_checkpoint=True): recompute each SpaceTimeBlock in backward (main_pretrain.py --use-checkpoint)")
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -109,10 +114,17 @@ def randomise_zero_init(model, seed=0):
                 p.fill_(0.5)
 
 
-def make_batch(batch, frames, seed):
+MODELS = {   # factory, image size, kwargs of flops_per_clip_train
+    "base": ("CLIP_OPENAI_TIMESFORMER_BASE", 224, dict(n=196, D=768, depth=12, p=16, W=512)),
+    "large": ("CLIP_OPENAI_TIMESFORMER_LARGE", 224, dict(n=256, D=1024, depth=24, p=14, W=768)),
+    "large336": ("CLIP_OPENAI_TIMESFORMER_LARGE_336PX", 336, dict(n=576, D=1024, depth=24, p=14, W=768)),
+}
+
+
+def make_batch(batch, frames, seed, size=224):
     import torch
     g = torch.Generator().manual_seed(seed)
-    x = torch.randn(batch, 3, frames, 224, 224, generator=g)
+    x = torch.randn(batch, 3, frames, size, size, generator=g)
     text = torch.zeros(batch, 77, dtype=torch.int64)
     for b in range(batch):
         ln = int(torch.randint(4, 21, (1,), generator=g))
@@ -150,7 +162,8 @@ def run_ours(args):
     from lavila_b200.models.loss import CLIPLoss
 
     torch.manual_seed(0)
-    model = M.CLIP_OPENAI_TIMESFORMER_BASE(num_frames=args.frames, project_embed_dim=256)
+    factory, img_size, flop_kw = MODELS[args.model]
+    model = getattr(M, factory)(num_frames=args.frames, project_embed_dim=256)
     randomise_zero_init(model)
     model.to(dev)
     crit = CLIPLoss(use_vissl=True, cache_labels=True, rank=rank, world_size=world)
@@ -160,13 +173,13 @@ def run_ours(args):
     opt = torch.optim.AdamW(param_groups(model), lr=3e-5, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01)
 
     B = args.batch
-    frames_h, text_h = make_batch(B, args.frames, 1234 + rank)
+    frames_h, text_h = make_batch(B, args.frames, 1234 + rank, img_size)
     frames_h, text_h = frames_h.pin_memory(), text_h.pin_memory()
     frames_d, text_d = frames_h.to(dev), text_h.to(dev)
 
     def step(fr, tx):
         opt.zero_grad(set_to_none=True)
-        out = net(fr, tx, use_checkpoint=False, norm_embed=True)
+        out = net(fr, tx, use_checkpoint=args.use_checkpoint, norm_embed=True)
         ld = crit(out)
         ld["loss"].backward()
         opt.step()
@@ -226,18 +239,21 @@ def run_ours(args):
     barrier()
 
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and args.model == "base":
         cpu = cpu_baseline(args.frames, budget_s=25.0)
 
     if rank == 0:
-        fl = flops_per_clip_train(T=args.frames)
+        fl = flops_per_clip_train(T=args.frames, **flop_kw)
         line = {
-            "metric": METRIC, "value": round(value, 3), "unit": "clips/s", "n_gpus": world, "steps": args.steps,
+            "metric": METRIC if args.model == "base" and args.frames == 16 else
+            "clips/sec dual-encoder pretrain %s %df x %d^2" % (factory, args.frames, img_size),
+            "value": round(value, 3), "unit": "clips/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": round(ms_step, 3), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "CLIP_OPENAI_TIMESFORMER_BASE dual-encoder pretrain step (fwd + CLIPLoss + bwd + AdamW), "
-                                   "%d frames x 224^2, batch %d per GPU" % (args.frames, B),
+            "config": {"workload": "%s dual-encoder pretrain step (fwd + CLIPLoss + bwd + AdamW), "
+                                   "%d frames x %d^2, batch %d per GPU" % (factory, args.frames, img_size, B),
                        "global_batch": B * world, "per_gpu_batch": B, "parallelism": "dp%d" % world,
+                       "use_checkpoint": bool(args.use_checkpoint),
                        "l2": "inputs (%.0f MB/step) and activations exceed the 126 MB L2; no explicit flush" % (frames_h.numel() * 4 / 1e6),
                        "weights": "random init (no network for checkpoints)",
                        "model_tflop_per_clip": round(fl / 1e12, 4),

@@ -220,17 +220,29 @@ class SpaceTimeBlockFn(torch.autograd.Function):
     the block input, 'frozen-in-time') -> QuickGELU MLP.  x: fp32 [B, N, D]."""
 
     @staticmethod
-    def forward(ctx, x, heads, frames, patches, eps, gate, *params):
+    def _run(x2, ps, dims, eps, gate):
+        xt, s_t = attn_sub_fwd(x2, x2, _attn_params(ps, "norm3", "timeattn"), dims, MODE_TIME, eps, gate=gate)
+        r, s_s = attn_sub_fwd(xt, x2, _attn_params(ps, "norm1", "attn"), dims, MODE_SPACE, eps)
+        y, s_m = mlp_sub_fwd(r, _mlp_params(ps), eps)
+        return y, s_t, s_s, s_m
+
+    @staticmethod
+    def forward(ctx, x, heads, frames, patches, eps, gate, checkpoint, *params):
         ps = dict(zip(BLOCK_PARAM_ORDER, params))
         B, N, D = x.shape
         x2 = x.contiguous().view(B * N, D)
         if x2.dtype != F32:
             x2 = x2.float()
         dims = dict(B=B, H=heads, T=frames, n=patches, N=N, L=0)
-        xt, s_t = attn_sub_fwd(x2, x2, _attn_params(ps, "norm3", "timeattn"), dims, MODE_TIME, eps, gate=gate)
-        r, s_s = attn_sub_fwd(xt, x2, _attn_params(ps, "norm1", "attn"), dims, MODE_SPACE, eps)
-        y, s_m = mlp_sub_fwd(r, _mlp_params(ps), eps)
-        ctx.saved = (s_t, s_s, s_m, ps, gate)
+        y, s_t, s_s, s_m = SpaceTimeBlockFn._run(x2, ps, dims, eps, gate)
+        if checkpoint:
+            # use_checkpoint=True (timesformer.py:175-190 checkpoints the two attentions; here the whole block): keep only
+            # the block input (4 bytes/element instead of ~50) and re-run the forward kernels in backward
+            ctx.saved = (None, None, None, ps, gate)
+            ctx.recompute = (x2, dims, eps)
+        else:
+            ctx.saved = (s_t, s_s, s_m, ps, gate)
+            ctx.recompute = None
         ctx.shape = (B, N, D)
         return y.view(B, N, D)
 
@@ -238,6 +250,11 @@ class SpaceTimeBlockFn(torch.autograd.Function):
     def backward(ctx, dy):
         s_t, s_s, s_m, ps, gate = ctx.saved
         ctx.saved = None
+        if ctx.recompute is not None:
+            x2, dims, eps = ctx.recompute
+            ctx.recompute = None
+            y, s_t, s_s, s_m = SpaceTimeBlockFn._run(x2, ps, dims, eps, gate)
+            del y
         B, N, D = ctx.shape
         dy = dy.contiguous().view(B * N, D)
         dy_b = take_bf16(dy)
@@ -257,7 +274,7 @@ class SpaceTimeBlockFn(torch.autograd.Function):
             "mlp.fc1.bias": g_m["fc1_b"], "mlp.fc2.weight": g_m["fc2_w"], "mlp.fc2.bias": g_m["fc2_b"],
         }
         dgate = g_t.get("gate") if gate is not None else None
-        return (dx.view(B, N, D), None, None, None, None, dgate) + tuple(grads[k] for k in BLOCK_PARAM_ORDER)
+        return (dx.view(B, N, D), None, None, None, None, dgate, None) + tuple(grads[k] for k in BLOCK_PARAM_ORDER)
 
 
 class LastBlockClsFn(torch.autograd.Function):

@@ -153,12 +153,12 @@ class SpaceTimeBlock(nn.Module):
 
     def forward(self, x, einops_from_space, einops_to_space, einops_from_time, einops_to_time, time_n, space_f,
                 use_checkpoint=False):
-        # use_checkpoint is accepted for API parity; the fused block already saves only bf16 operands + fp32 residuals.
+        # use_checkpoint: the block keeps only its input and re-runs its forward kernels in backward (engine.py)
         if self.attention_style != 'frozen-in-time':
             raise NotImplementedError
         gate = getattr(self, "alpha_timeattn", None)
         return E.SpaceTimeBlockFn.apply(x, self.num_heads, int(space_f), int(time_n), float(self.norm1.eps), gate,
-                                        *self._params())
+                                        bool(use_checkpoint) and torch.is_grad_enabled(), *self._params())
 
 
 class SpaceTimeTransformer(nn.Module):

@@ -158,3 +158,25 @@ def test_clip_tsf_l14_geometry_vs_oracle():
             continue
         r, cs = rel_l2(g, want), cosine(g, want)
         assert cs > 0.99 and r < 6e-2, "%s: rel_l2 %.3e cosine %.5f" % (name, r, cs)
+
+
+def test_use_checkpoint_recompute_matches():
+    """model(..., use_checkpoint=True) (main_pretrain.py:494, timesformer.py:175-190): blocks keep only their input and
+    re-run their forward kernels in backward; outputs are identical and gradients agree with the saved-activation path
+    (split-K atomics make weight gradients order-dependent in the last bits, hence 1e-5)."""
+    from lavila_b200.models.loss import CLIPLoss
+    cfg = GOLD["norm"]["cfg"]
+    params = O.init_params(cfg, seed=3)
+    frames, text = O.synthetic_batch(cfg, 4, seed=9)
+    frames, text = frames.to(DEV), text.to(DEV)
+    res = []
+    for ck in (False, True):
+        model = build_clip(cfg, params)
+        model.visual.cls_only_tail = False
+        out = model(frames, text, use_checkpoint=ck, norm_embed=True)
+        CLIPLoss()(out)["loss"].backward()
+        res.append((out["image_embed"].detach().clone(), {k: v.grad.clone() for k, v in model.named_parameters() if v.grad is not None}))
+    assert torch.equal(res[0][0], res[1][0])
+    assert res[0][1].keys() == res[1][1].keys()
+    for k in res[0][1]:
+        assert rel_l2(res[1][1][k], res[0][1][k]) < 1e-5, k
