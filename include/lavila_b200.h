@@ -192,6 +192,18 @@ int lv_clip_loss_bwd(const float* img, const float* txt, const float* scale_ptr,
                      const float* lse_txt, const float* gout, float grad_scale, float scale_grad_scale, int Ng, int E,
                      int r0, int Nl, float* d_img, float* d_txt, float* d_scale, void* stream);
 
+/* Multi-GPU CLIPLoss forward with the embedding all-gather fused into the kernel (replaces gather_from_all x2 +
+ * the logits/CE chain, lavila/models/loss.py:74-79,107-116 and distributed_utils.py:51-62).  `peers` is a DEVICE array of W
+ * pointers to the ranks' symmetric (NVLink peer-mapped) blocks, each 2 slots of [Bl x 2E fp32 = image | text][32 words,
+ * word 0 = ready flag]; `step` (> 0, +1 per call on every rank) selects slot step & 1 and is the flag value.  The kernel
+ * publishes this rank's rows, pulls every other rank's rows over NVLink into all_img / all_txt [W*Bl, E] (kept for the
+ * backward, which is lv_clip_loss_bwd on those buffers) and evaluates the global loss: result[0] = loss, result[1] = acc.
+ * ctrl: uint32[4], zeroed once.  Launched cooperatively (W*Bl CTAs must be co-resident).  A peer that never publishes
+ * makes the loss NaN after a bounded spin instead of hanging. */
+int lv_clip_loss_fwd_gather(const float* img_local, const float* txt_local, void* const* peers, int rank, int W, int Bl,
+                            uint32_t step, float* all_img, float* all_txt, const float* scale_ptr, int E, float* lse_img,
+                            float* lse_txt, float* partial, uint32_t* ctrl, float* result, void* stream);
+
 /* SSLCLIPLoss (lavila/models/loss.py:148-213): gt[i] = 1 human narration / 0 pseudo narration; pair scale
  * c(i,j) = *scale_pseudo_ptr (0 + 0) | sqrt(*scale_pseudo_ptr * *scale_ptr) (0 + 1) | *scale_ptr (1 + 1), both pointers hold the
  * already exponentiated scales.  result[6] = {loss, clip_acc, clip_acc_gt, clip_acc_pseudo, num_gt, num_pseudo} (an empty

@@ -341,6 +341,179 @@ ssl_clip_loss_bwd_kernel(const float* __restrict__ img, const float* __restrict_
   }
 }
 
+// ================================================================================================ fused gather + loss
+// Multi-GPU CLIPLoss forward with the embedding all-gather INSIDE the kernel (loss.py:76-79 + distributed_utils.py:51-62):
+// every rank owns a symmetric block (NVLink peer-mapped on all ranks) of two slots (step parity), each
+//   [Bl rows x 2E fp32 = image | text][32-word pad, word 0 = ready flag].
+// One kernel per rank, launched cooperatively with Ng = W*Bl CTAs:
+//   phase 0  CTAs of this rank's own rows publish their row into the rank's symmetric slot; the last one releases the
+//            slot flag (= step) at system scope;
+//   phase 1  CTA i acquires the flag of the rank that owns global row i (spin on the peer's memory over NVLink), pulls
+//            that row (2E floats, peer loads) into the local gathered buffers all_img / all_txt;
+//   phase 2  grid barrier, then exactly the single-GPU loss of clip_loss_fwd_kernel on the gathered rows.
+// NVLink traffic is the minimum (every remote row crosses once); no NCCL call, no gathered staging copy, no host sync.
+// Slot reuse is safe: a rank rewrites slot s two steps later, and every peer has passed DDP's gradient all-reduce of the
+// step in between.  A peer that never publishes (crashed rank) makes the spin time out: result = NaN, no hang.
+__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned int ld_volatile_u32(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ float ld_relaxed_sys_f32(const float* p) {
+  float v;
+  asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+  return v;
+}
+
+constexpr int P2P_PAD = 32;   // floats after the data of a slot; word 0 = flag
+
+// ctrl[0] = last-CTA counter (as clip_loss_fwd_kernel), ctrl[1] = own-rows-published counter, ctrl[2] = grid-barrier
+// arrivals, ctrl[3] = grid-barrier generation.  All zero before the first call; self-resetting.
+__global__ void __launch_bounds__(THREADS)
+clip_loss_fwd_gather_kernel(const float* __restrict__ img_local, const float* __restrict__ txt_local,
+                            float* const* __restrict__ peers, int rank, int W, int Bl, unsigned int step,
+                            float* __restrict__ all_img, float* __restrict__ all_txt, const float* __restrict__ scale_ptr,
+                            int E, float* __restrict__ lse_img, float* __restrict__ lse_txt, float* __restrict__ partial,
+                            unsigned int* __restrict__ ctrl, float* __restrict__ result) {
+  extern __shared__ float sm[];
+  float* a_img = sm;
+  float* a_txt = sm + E;
+  float* vals = sm + 2 * E;
+  __shared__ float sred[THREADS / 32];
+  __shared__ int ired[THREADS / 32];
+  __shared__ bool is_last;
+  __shared__ int timed_out;
+  const int Ng = W * Bl;
+  const int i = blockIdx.x, tid = threadIdx.x;
+  const int owner = i / Bl, lrow = i - owner * Bl;
+  const long long slot_floats = (long long)Bl * 2 * E + P2P_PAD;
+  const long long slot_off = (long long)(step & 1u) * slot_floats;
+  if (tid == 0) timed_out = 0;
+  // ---- phase 0: publish own rows
+  if (owner == rank) {
+    float* mine = peers[rank] + slot_off + (long long)lrow * 2 * E;
+    for (int c = tid; c < E; c += THREADS) {
+      const float a = img_local[(long long)lrow * E + c], b = txt_local[(long long)lrow * E + c];
+      mine[c] = a;
+      mine[E + c] = b;
+      all_img[(long long)i * E + c] = a;
+      all_txt[(long long)i * E + c] = b;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid == 0) {
+      const unsigned int done = atomicAdd(ctrl + 1, 1u);
+      if (done == (unsigned)Bl - 1) {
+        ctrl[1] = 0;
+        __threadfence_system();
+        st_release_sys(reinterpret_cast<unsigned int*>(peers[rank] + slot_off + (long long)Bl * 2 * E), step);
+      }
+    }
+  } else {
+    // ---- phase 1: wait for the owner's slot, pull the row over NVLink
+    const float* theirs = peers[owner] + slot_off;
+    if (tid == 0) {
+      const unsigned int* flag = reinterpret_cast<const unsigned int*>(theirs + (long long)Bl * 2 * E);
+      long long spins = 0;
+      while (ld_acquire_sys(flag) != step) {
+        __nanosleep(200);
+        if (++spins > (1ll << 24)) { timed_out = 1; break; }   // ~3+ s: a peer is gone; fail loudly instead of hanging
+      }
+    }
+    __syncthreads();
+    const float* row = theirs + (long long)lrow * 2 * E;
+    for (int c = tid; c < E; c += THREADS) {
+      all_img[(long long)i * E + c] = ld_relaxed_sys_f32(row + c);
+      all_txt[(long long)i * E + c] = ld_relaxed_sys_f32(row + E + c);
+    }
+  }
+  // ---- grid barrier (all Ng CTAs are co-resident: cooperative launch)
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    const unsigned int gen = ld_volatile_u32(ctrl + 3);
+    if (atomicAdd(ctrl + 2, 1u) == (unsigned)Ng - 1) {
+      ctrl[2] = 0;
+      __threadfence();
+      atomicAdd(ctrl + 3, 1u);
+    } else {
+      while (ld_volatile_u32(ctrl + 3) == gen) __nanosleep(100);
+    }
+    __threadfence();
+  }
+  __syncthreads();
+  // ---- phase 2: the single-GPU loss on the gathered rows (plain loads: the rows were written by other CTAs of this kernel)
+  const float s = __ldg(scale_ptr);
+  for (int c = tid; c < E; c += THREADS) {
+    a_img[c] = s * __ldcg(all_img + (long long)i * E + c);
+    a_txt[c] = __ldcg(all_txt + (long long)i * E + c);
+  }
+  __syncthreads();
+  for (int j = tid; j < Ng; j += THREADS) {
+    const float* b = all_txt + (long long)j * E;
+    float acc = 0.f;
+    for (int c = 0; c < E; c += 4) {
+      const float4 x = *reinterpret_cast<const float4*>(a_img + c);
+      const float4 y = __ldcg(reinterpret_cast<const float4*>(b + c));
+      acc += x.x * y.x + x.y * y.y + x.z * y.z + x.w * y.w;
+    }
+    vals[j] = acc;
+  }
+  __syncthreads();
+  const RowStat ri = row_stats(vals, Ng, i, sred, ired);
+  __syncthreads();
+  for (int j = tid; j < Ng; j += THREADS) {
+    const float* b = all_img + (long long)j * E;
+    float acc = 0.f;
+    for (int c = 0; c < E; c += 4) {
+      const float4 x = *reinterpret_cast<const float4*>(a_txt + c);
+      const float4 y = __ldcg(reinterpret_cast<const float4*>(b + c));
+      acc += x.x * y.x + x.y * y.y + x.z * y.z + x.w * y.w;
+    }
+    vals[j] = s * acc;
+  }
+  __syncthreads();
+  const RowStat rt = row_stats(vals, Ng, i, sred, ired);
+  if (tid == 0) {
+    lse_img[i] = ri.lse;
+    lse_txt[i] = rt.lse;
+    partial[2 * i] = timed_out ? NAN : 0.5f * ((ri.lse - ri.label_logit) + (rt.lse - rt.label_logit));
+    partial[2 * i + 1] = (ri.argmax == i) ? 1.f : 0.f;
+    __threadfence();
+    const unsigned int done = atomicAdd(ctrl, 1u);
+    is_last = (done == (unsigned)Ng - 1);
+  }
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    float l = 0.f, a = 0.f;
+    for (int j = tid; j < Ng; j += THREADS) {
+      l += __ldcg(partial + 2 * j);
+      a += __ldcg(partial + 2 * j + 1);
+    }
+    l = warp_sum(l);
+    a = warp_sum(a);
+    __shared__ float lr[THREADS / 32], ar[THREADS / 32];
+    if ((tid & 31) == 0) { lr[tid >> 5] = l; ar[tid >> 5] = a; }
+    __syncthreads();
+    if (tid == 0) {
+      float Lsum = 0.f, A = 0.f;
+      for (int w = 0; w < THREADS / 32; ++w) { Lsum += lr[w]; A += ar[w]; }
+      result[0] = Lsum / Ng;
+      result[1] = 100.f * A / Ng;
+      ctrl[0] = 0;
+    }
+  }
+}
+
 }  // namespace loss
 }  // namespace lv
 
@@ -390,4 +563,28 @@ extern "C" int lv_ssl_clip_loss_bwd(const float* img, const float* txt, const fl
   LV_REQUIRE(smem <= 48 * 1024, "lv_ssl_clip_loss_bwd: Ng too large");
   loss::ssl_clip_loss_bwd_kernel<<<2 * Nl, loss::THREADS, smem, (cudaStream_t)stream>>>(img, txt, scale_ptr, scale_pseudo_ptr, gt, lse_img, lse_txt, gout, grad_scale, scale_grad_scale, Ng, E, r0, Nl, d_img, d_txt, d_scales);
   return check_launch("lv_ssl_clip_loss_bwd");
+}
+
+extern "C" int lv_clip_loss_fwd_gather(const float* img_local, const float* txt_local, void* const* peers, int rank, int W,
+                                       int Bl, uint32_t step, float* all_img, float* all_txt, const float* scale_ptr, int E,
+                                       float* lse_img, float* lse_txt, float* partial, uint32_t* ctrl, float* result,
+                                       void* stream) {
+  LV_REQUIRE(img_local && txt_local && peers && all_img && all_txt && scale_ptr && lse_img && lse_txt && partial && ctrl && result,
+             "lv_clip_loss_fwd_gather: null pointer");
+  LV_REQUIRE(W > 0 && rank >= 0 && rank < W && Bl > 0 && E > 0 && E % 4 == 0 && step > 0, "lv_clip_loss_fwd_gather: bad arguments");
+  int Ng = W * Bl;
+  const size_t smem = (size_t)(2 * E + Ng) * sizeof(float);
+  LV_REQUIRE(smem <= 48 * 1024, "lv_clip_loss_fwd_gather: Ng=%d too large for one CTA row buffer", Ng);
+  int per_sm = 0;
+  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, loss::clip_loss_fwd_gather_kernel, loss::THREADS, smem);
+  if (e != cudaSuccess) return set_error((int)e, "lv_clip_loss_fwd_gather: occupancy query: %s", cudaGetErrorString(e));
+  LV_REQUIRE((long long)per_sm * sm_count() >= Ng, "lv_clip_loss_fwd_gather: %d CTAs cannot be co-resident (%d per SM)", Ng, per_sm);
+  float* const* peers_f = reinterpret_cast<float* const*>(peers);
+  void* args[] = {(void*)&img_local, (void*)&txt_local, (void*)&peers_f, (void*)&rank, (void*)&W, (void*)&Bl, (void*)&step,
+                  (void*)&all_img, (void*)&all_txt, (void*)&scale_ptr, (void*)&E, (void*)&lse_img, (void*)&lse_txt,
+                  (void*)&partial, (void*)&ctrl, (void*)&result};
+  e = cudaLaunchCooperativeKernel((const void*)loss::clip_loss_fwd_gather_kernel, dim3(Ng), dim3(loss::THREADS), args, smem,
+                                  (cudaStream_t)stream);
+  if (e != cudaSuccess) return set_error((int)e, "lv_clip_loss_fwd_gather: cooperative launch: %s", cudaGetErrorString(e));
+  return check_launch("lv_clip_loss_fwd_gather");
 }

@@ -80,3 +80,34 @@ def gather_embeddings_gt(image_features, text_features, gt_indicators, world_siz
     dist.all_gather(buf, local)
     allb = torch.stack(buf, 0).view(world_size * B, 2 * E + 1)
     return allb[:, :E].contiguous(), allb[:, E:2 * E].contiguous(), allb[:, 2 * E].contiguous()
+
+
+class PeerEmbeddingExchange:
+    """Symmetric (NVLink peer-mapped) staging blocks for the fused gather + loss kernel (csrc/clip_loss.cu): every rank owns
+    2 slots x ([B x 2E fp32] + 32 flag words); all ranks hold device pointers to all blocks.  Built on
+    torch.distributed._symmetric_memory (CUDA VMM + fabric handles over NVLink/NVSwitch); torch only allocates and exchanges
+    the handles -- the data movement is the kernel's own peer loads."""
+    PAD = 32
+
+    def __init__(self, B, E, device, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+        group = group if group is not None else dist.group.WORLD
+        try:
+            symm_mem.enable_symm_mem_for_group(group.group_name)
+        except Exception:
+            pass
+        self.B, self.E = B, E
+        self.slot_floats = B * 2 * E + self.PAD
+        self.buf = symm_mem.empty(2 * self.slot_floats, dtype=torch.float32, device=device)
+        self.buf.zero_()
+        self.handle = symm_mem.rendezvous(self.buf, group)
+        self.peers_dev = int(self.handle.buffer_ptrs_dev)
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.ctrl = torch.zeros(4, device=device, dtype=torch.int32)
+        self.step = 0
+        torch.cuda.synchronize(device)
+        dist.barrier(group)          # nobody polls a flag before every block is zeroed
+
+    def next_step(self):
+        self.step += 1
+        return self.step

@@ -133,8 +133,11 @@ class GPT2Block(nn.Module):
         _linear(a, mlp.c_proj, M, out, flags=fl, resid=h, scale=gate)
         return out
 
-    def forward_rows(self, h, B, Lq, ctx_kv_cache, ctx_bf16, ctx_rows):
-        """h: fp32 [B*Lq, H] residual stream.  ctx_bf16: bf16 [B*ctx_rows, H] (already cast) or None."""
+    def forward_rows(self, h, B, Lq, ctx_kv_cache, ctx_bf16, ctx_rows, self_kv_cache=None, past_len=0):
+        """h: fp32 [B*Lq, H] residual stream.  ctx_bf16: bf16 [B*ctx_rows, H] (already cast) or None.
+        self_kv_cache (dict with "max_len", filled per layer) + past_len: incremental decoding -- the rows are positions
+        past_len .. past_len+Lq-1, their keys/values are appended to the layer's cache and attention runs over the
+        past_len+Lq cached keys (same numbers as re-running the whole prefix, gpt2_gated.py:331-345 `layer_past`)."""
         M, H = h.shape
         heads = self.attn.num_heads
         dev = h.device
@@ -162,8 +165,19 @@ class GPT2Block(nn.Module):
         qkv = torch.empty(M, 3 * H, device=dev, dtype=BF16)
         _linear(y, self.attn.c_attn, M, qkv)
         att = torch.empty(M, H, device=dev, dtype=BF16)
-        ops.flash_attn_fwd(qkv, qkv[:, H:], qkv[:, 2 * H:], att, B, heads, Lq, Lq, q_rows=Lq, kv_rows=Lq, ld_q=3 * H,
-                           ld_kv=3 * H, ld_out=H, causal=True)
+        if self_kv_cache is None:
+            ops.flash_attn_fwd(qkv, qkv[:, H:], qkv[:, 2 * H:], att, B, heads, Lq, Lq, q_rows=Lq, kv_rows=Lq, ld_q=3 * H,
+                               ld_kv=3 * H, ld_out=H, causal=True)
+        else:
+            Lmax = self_kv_cache["max_len"]
+            kv = self_kv_cache.get(self.layer_idx)
+            if kv is None:
+                kv = torch.zeros(B, Lmax, 2 * H, device=dev, dtype=BF16)
+                self_kv_cache[self.layer_idx] = kv
+            kv[:, past_len:past_len + Lq].copy_(qkv.view(B, Lq, 3 * H)[:, :, H:])
+            kv2 = kv.view(B * Lmax, 2 * H)
+            ops.flash_attn_fwd(qkv, kv2, kv2[:, H:], att, B, heads, Lq, past_len + Lq, q_rows=Lq, kv_rows=Lmax, ld_q=3 * H,
+                               ld_kv=2 * H, ld_out=H, causal=True)
         h2 = torch.empty(M, H, device=dev, dtype=F32)
         _linear(att, self.attn.c_proj, M, h2, flags=L.EPI_RESID, resid=h)
         return self._ffn(h2, self.ln_2, self.mlp, M, H, L.EPI_GELU_TANH, None)
@@ -182,19 +196,21 @@ class GPT2Model(nn.Module):
         self.ln_f = nn.LayerNorm(self.embed_dim, eps=getattr(config, "layer_norm_epsilon", 1e-5))
 
     @torch.no_grad()
-    def forward_rows(self, input_ids, encoder_hidden_states=None, ctx_kv_cache=None):
+    def forward_rows(self, input_ids, encoder_hidden_states=None, ctx_kv_cache=None, self_kv_cache=None, past_len=0):
         B, Lq = input_ids.shape
         H = self.embed_dim
         dev = self.wte.weight.device
         h = torch.empty(B * Lq, H, device=dev, dtype=F32)
-        ops.text_embed(input_ids.contiguous(), self.wte.weight, self.wpe.weight, h, B * Lq, Lq, H, self.wte.weight.shape[0])
+        # positions past_len .. past_len+Lq-1 (gpt2_gated.py:855-858 position_ids with past_length)
+        ops.text_embed(input_ids.contiguous(), self.wte.weight, self.wpe.weight[past_len:], h, B * Lq, Lq, H,
+                       self.wte.weight.shape[0])
         ctx_b, ctx_rows = None, 0
         if encoder_hidden_states is not None:
             ctx_rows = encoder_hidden_states.shape[1]
             ctx_b = ops.cast_bf16(encoder_hidden_states.contiguous().float().view(-1, H))
         cache = ctx_kv_cache if ctx_kv_cache is not None else {}
         for blk in self.h:
-            h = blk.forward_rows(h, B, Lq, cache, ctx_b, ctx_rows)
+            h = blk.forward_rows(h, B, Lq, cache, ctx_b, ctx_rows, self_kv_cache, past_len)
         y = torch.empty(B * Lq, H, device=dev, dtype=BF16)
         ops.layernorm_fwd(h, self.ln_f.weight, self.ln_f.bias, self.ln_f.eps, B * Lq, H, y_bf16=y)
         return y
@@ -242,11 +258,13 @@ class GPT2LMHeadModel(nn.Module):
         return self._head_bf16, V, Vp
 
     @torch.no_grad()
-    def forward(self, input_ids=None, encoder_hidden_states=None, last_only=False, ctx_kv_cache=None, **kwargs):
-        """Returns an object with `.logits` [B, L, vocab] fp32 (or [B, 1, vocab] with last_only=True)."""
+    def forward(self, input_ids=None, encoder_hidden_states=None, last_only=False, ctx_kv_cache=None, self_kv_cache=None,
+                past_len=0, **kwargs):
+        """Returns an object with `.logits` [B, L, vocab] fp32 (or [B, 1, vocab] with last_only=True).
+        With self_kv_cache, input_ids holds only the NEW positions past_len .. past_len+L-1."""
         B, Lq = input_ids.shape
         H = self.transformer.embed_dim
-        y = self.transformer.forward_rows(input_ids, encoder_hidden_states, ctx_kv_cache)
+        y = self.transformer.forward_rows(input_ids, encoder_hidden_states, ctx_kv_cache, self_kv_cache, past_len)
         wb, V, Vp = self._padded_head()
         if last_only:
             y = y.view(B, Lq, H)[:, -1].contiguous()

@@ -36,6 +36,35 @@ def gather_features(image_features, text_features, local_loss=False, gather_with
     return all_image, all_text
 
 
+def _peer_exchange(state, B, E, dev):
+    """The symmetric-memory blocks of the fused gather + loss kernel, created on first use (collective).  Disabled with
+    LAVILA_B200_P2P_LOSS=0 (then: one NCCL all_gather + the single-GPU loss kernel)."""
+    import os
+    if os.environ.get("LAVILA_B200_P2P_LOSS", "1") == "0" or dev.type != "cuda":
+        return None
+    if state.get("xch_unavailable"):
+        return None
+    x = state.get("xch")
+    if x is None or x.B != B or x.E != E:
+        import torch.distributed as dist
+        from .distributed_utils import PeerEmbeddingExchange
+        err = None
+        try:
+            x = PeerEmbeddingExchange(B, E, dev)
+        except Exception as e:   # no peer access / no symmetric-memory support on this box
+            x, err = None, e
+        ok = torch.tensor([0 if x is None else 1], device=dev, dtype=torch.int32)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)     # all ranks take the same path
+        if int(ok.item()) == 0:
+            if dist.get_rank() == 0:
+                print("lavila_b200: symmetric-memory peer exchange unavailable (%r); CLIPLoss uses one NCCL all_gather" % (err,))
+            state["xch_unavailable"] = True
+            state["xch"] = None
+            return None
+        state["xch"] = x
+    return x
+
+
 class _ClipLossFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, image, text, logit_scale, rank, world_size, grad_scale, state):
@@ -43,19 +72,27 @@ class _ClipLossFn(torch.autograd.Function):
         text = text.contiguous().float()
         B, E = image.shape
         dev = image.device
-        if world_size > 1:
-            all_i, all_t = gather_embeddings(image, text, world_size)
-        else:
-            all_i, all_t = image, text
-        Ng = all_i.shape[0]
         scale = logit_scale.detach().reshape(1).contiguous().float()
+        Ng = B * world_size
         lse_i = torch.empty(Ng, device=dev, dtype=F32)
         lse_t = torch.empty(Ng, device=dev, dtype=F32)
         partial = torch.empty(2 * Ng, device=dev, dtype=F32)
         result = torch.empty(2, device=dev, dtype=F32)
-        if state.get("counter") is None or state["counter"].device != dev:
-            state["counter"] = torch.zeros(1, device=dev, dtype=torch.int32)
-        ops.clip_loss_fwd(all_i, all_t, scale, Ng, E, lse_i, lse_t, partial, state["counter"], result)
+        xch = _peer_exchange(state, B, E, dev) if world_size > 1 else None
+        if xch is not None:
+            # ONE kernel: publish own rows -> pull the peers' rows over NVLink -> global loss (csrc/clip_loss.cu)
+            all_i = torch.empty(Ng, E, device=dev, dtype=F32)
+            all_t = torch.empty(Ng, E, device=dev, dtype=F32)
+            ops.clip_loss_fwd_gather(image, text, xch.peers_dev, rank, world_size, B, xch.next_step(), all_i, all_t, scale, E,
+                                     lse_i, lse_t, partial, xch.ctrl, result)
+        else:
+            if world_size > 1:
+                all_i, all_t = gather_embeddings(image, text, world_size)     # NCCL all_gather (LAVILA_B200_P2P_LOSS=0)
+            else:
+                all_i, all_t = image, text
+            if state.get("counter") is None or state["counter"].device != dev:
+                state["counter"] = torch.zeros(1, device=dev, dtype=torch.int32)
+            ops.clip_loss_fwd(all_i, all_t, scale, Ng, E, lse_i, lse_t, partial, state["counter"], result)
         ctx.saved = (all_i, all_t, scale, lse_i, lse_t)
         ctx.meta = (B, E, Ng, rank, world_size, grad_scale)
         ctx.mark_non_differentiable(result[1])

@@ -48,8 +48,10 @@ class VCLM_HF(nn.Module):
         return {'text_tokens_logits': logits.permute(0, 2, 1), 'labels': labels}
 
     def generate(self, image_tokens, tokenizer, target=None, max_text_length=77, top_k=None, top_p=None,
-                 num_return_sequences=1, temperature=1.0, teacher_forcing=False, early_stopping=False):
-        """narrator.py:106-147."""
+                 num_return_sequences=1, temperature=1.0, teacher_forcing=False, early_stopping=False, use_kv_cache=True):
+        """narrator.py:106-147.  Same sampling loop; the decoder is evaluated incrementally (use_kv_cache: self-attention
+        keys/values of the prefix and the cross-attention K/V of the clip are cached, the LM head sees the last position
+        only) instead of re-running the whole prefix every step -- the logits, hence the sampled ids, are the same."""
         image_tokens = image_tokens.repeat_interleave(num_return_sequences, dim=0)
         device = image_tokens.device
         generated_text_ids = torch.LongTensor([[tokenizer.bos_token_id]] * image_tokens.shape[0]).to(device)
@@ -58,10 +60,15 @@ class VCLM_HF(nn.Module):
         nlls, num_tokens = torch.zeros(image_tokens.shape[0]).to(device), torch.zeros(image_tokens.shape[0]).to(device)
         is_reach_eos = torch.zeros(image_tokens.shape[0]).bool().to(device)
         kv_cache = {}
+        self_cache = {"max_len": max_text_length} if (use_kv_cache and not teacher_forcing) else None
         with torch.no_grad():
             for i in range(max_text_length - 1):
-                out = self.text_decoder(condition_text_ids, encoder_hidden_states=image_tokens, last_only=True,
-                                        ctx_kv_cache=kv_cache)
+                if self_cache is not None:
+                    out = self.text_decoder(condition_text_ids[:, -1:], encoder_hidden_states=image_tokens, last_only=True,
+                                            ctx_kv_cache=kv_cache, self_kv_cache=self_cache, past_len=i)
+                else:
+                    out = self.text_decoder(condition_text_ids, encoder_hidden_states=image_tokens, last_only=True,
+                                            ctx_kv_cache=kv_cache)
                 next_token_logits = out.logits[:, -1, :]
                 if target is not None:
                     nll = F.cross_entropy(next_token_logits, target[:, i + 1], ignore_index=tokenizer.pad_token_id, reduction='none')

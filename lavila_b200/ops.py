@@ -243,3 +243,12 @@ def ssl_clip_loss_bwd(img, txt, scale, scale_pseudo, gt, lse_img, lse_txt, gout,
                                       float(grad_scale), float(scale_grad_scale), Ng, E, r0, Nl, d_img.data_ptr(),
                                       d_txt.data_ptr(), _p(d_scales), _stream())
     L.check(rc, "lv_ssl_clip_loss_bwd")
+
+
+def clip_loss_fwd_gather(img_local, txt_local, peers_dev_ptr, rank, W, Bl, step, all_img, all_txt, scale, E, lse_img, lse_txt,
+                         partial, ctrl, result):
+    """Fused NVLink gather + loss forward (lv_clip_loss_fwd_gather).  peers_dev_ptr: int, device address of the W-pointer array."""
+    rc = L.lib().lv_clip_loss_fwd_gather(img_local.data_ptr(), txt_local.data_ptr(), int(peers_dev_ptr), rank, W, Bl, int(step),
+                                         all_img.data_ptr(), all_txt.data_ptr(), scale.data_ptr(), E, lse_img.data_ptr(),
+                                         lse_txt.data_ptr(), partial.data_ptr(), ctrl.data_ptr(), result.data_ptr(), _stream())
+    L.check(rc, "lv_clip_loss_fwd_gather")

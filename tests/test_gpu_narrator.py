@@ -79,6 +79,30 @@ def test_generate_runs_like_reference():
     assert torch.equal(torch.isinf(w), torch.isinf(ON.warp_logits(logits, 0.7, 0.95)))
 
 
+def test_kv_cached_decoding_equals_full_prefix():
+    """Incremental decoding (self-attention KV cache) gives the logits of the reference algorithm (full
+    prefix re-forward, narrator.py:118-121) position by position, and generate() samples the same ids with and without it."""
+    cfg, m, frames = _setup()
+    tok = m.encode_image(frames)
+    ids = GOLD["text"][:, :6].contiguous().to(DEV)
+    full = m.text_decoder(ids, encoder_hidden_states=tok).logits                      # [B, 6, V]
+    cache, ctx = {"max_len": 8}, {}
+    # prefill 3 positions at once, then one position at a time
+    got = [m.text_decoder(ids[:, :3].contiguous(), encoder_hidden_states=tok, ctx_kv_cache=ctx, self_kv_cache=cache, past_len=0).logits]
+    for t in range(3, 6):
+        got.append(m.text_decoder(ids[:, t:t + 1].contiguous(), encoder_hidden_states=tok, ctx_kv_cache=ctx, self_kv_cache=cache,
+                                  past_len=t).logits)
+    got = torch.cat(got, 1)
+    assert rel_l2(got, full) < 1e-5, rel_l2(got, full)
+    t = SimpleNamespace(bos_token_id=cfg["vocab_size"] - 1, eos_token_id=cfg["vocab_size"] - 1, pad_token_id=0)
+    outs = []
+    for use in (False, True):
+        torch.manual_seed(5)
+        outs.append(m.generate(tok, t, max_text_length=8, top_p=0.95, temperature=0.7, num_return_sequences=3, use_kv_cache=use))
+    assert torch.equal(outs[0][0], outs[1][0])
+    assert rel_l2(outs[1][1], outs[0][1]) < 1e-4
+
+
 @pytest.mark.parametrize("B,H,Lq,Lk,mqa,causal", [(2, 3, 5, 40, False, False), (2, 25, 77, 256, False, False),
                                                    (3, 4, 77, 77, False, True), (2, 12, 256, 785, True, False),
                                                    (1, 2, 1, 1, False, True), (2, 2, 130, 130, False, True)])

@@ -18,11 +18,12 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=32)
-    ap.add_argument("--returns", type=int, default=1)
+    ap.add_argument("--returns", default="1", help="num_return_sequences; comma list = several runs with one model")
     ap.add_argument("--frames", type=int, default=4)
     ap.add_argument("--max-len", type=int, default=77)
     ap.add_argument("--impl", default="ours", choices=["ours", "eager"])
     ap.add_argument("--decoder", default="xl", choices=["xl", "base"])
+    ap.add_argument("--no-kv-cache", action="store_true", help="ours: re-run the whole prefix every step (reference algorithm)")
     ap.add_argument("--encoder", default="base", choices=["base", "large"],
                     help="large = TSF-L/14 224px: VCLM_OPENAI_TIMESFORMER_LARGE_GPT2_XL, the model BASELINE config 4 names")
     a = ap.parse_args()
@@ -46,7 +47,7 @@ def main():
         def run():
             t = model.encode_image(frames)
             return model.generate(t, tok, max_text_length=a.max_len, top_p=0.95, temperature=0.7,
-                                  num_return_sequences=a.returns, early_stopping=False)
+                                  num_return_sequences=R, early_stopping=False, use_kv_cache=not a.no_kv_cache)
     else:
         from oracle import narrator as ON
         H, Ld, nh, freq = (1600, 48, 25, 2) if a.decoder == "xl" else (768, 12, 12, 1)
@@ -61,24 +62,25 @@ def main():
 
         def run():   # the reference algorithm: no caches, full re-forward and full LM head every step
             with torch.no_grad():
-                t = ON.vclm_encode_image(frames, p, cfg).repeat_interleave(a.returns, 0)
+                t = ON.vclm_encode_image(frames, p, cfg).repeat_interleave(R, 0)
                 ids = torch.full((t.shape[0], 1), 50256, dtype=torch.int64, device=dev)
                 for _ in range(a.max_len - 1):
                     lg = ON.gpt2_lm_logits(ids, t, p, cfg)[:, -1]
                     pr = torch.softmax(ON.warp_logits(lg, 0.7, 0.95), dim=-1)
                     ids = torch.cat((ids, torch.multinomial(pr, 1)), 1)
                 return ids, None
-    run()
-    torch.cuda.synchronize()
-    t0 = time.time()
-    ids, _ = run()
-    torch.cuda.synchronize()
-    dt = time.time() - t0
-    print(json.dumps({"impl": a.impl, "encoder": a.encoder, "decoder": a.decoder, "batch": a.batch, "returns": a.returns, "frames": a.frames,
-                      "tokens": int(ids.shape[1]), "seconds": round(dt, 3), "clips_per_s": round(a.batch / dt, 3),
-                      "sequences_per_s": round(a.batch * a.returns / dt, 3),
-                      "max_mem_gb": round(torch.cuda.max_memory_allocated() / 2 ** 30, 1)}))
-
+    for R in [int(x) for x in str(a.returns).split(",")]:
+        run()
+        torch.cuda.synchronize()
+        t0 = time.time()
+        ids, _ = run()
+        torch.cuda.synchronize()
+        dt = time.time() - t0
+        print(json.dumps({"impl": a.impl, "encoder": a.encoder, "decoder": a.decoder, "kv_cache": (a.impl == "ours" and not a.no_kv_cache),
+                          "batch": a.batch, "returns": R, "frames": a.frames,
+                          "tokens": int(ids.shape[1]), "seconds": round(dt, 3), "clips_per_s": round(a.batch / dt, 3),
+                          "sequences_per_s": round(a.batch * R / dt, 3),
+                          "max_mem_gb": round(torch.cuda.max_memory_allocated() / 2 ** 30, 1)}), flush=True)
 
 if __name__ == "__main__":
     main()
