@@ -163,7 +163,9 @@ def run_ours(args):
 
     torch.manual_seed(0)
     factory, img_size, flop_kw = MODELS[args.model]
-    model = getattr(M, factory)(num_frames=args.frames, project_embed_dim=256)
+    import contextlib
+    with contextlib.redirect_stdout(sys.stderr):     # the factories print like the reference's; stdout carries ONE JSON line
+        model = getattr(M, factory)(num_frames=args.frames, project_embed_dim=256)
     randomise_zero_init(model)
     model.to(dev)
     crit = CLIPLoss(use_vissl=True, cache_labels=True, rank=rank, world_size=world)

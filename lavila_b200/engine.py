@@ -61,6 +61,58 @@ def take_bf16(t_f32):
     return ops.cast_bf16(t_f32.reshape(-1)).view(t_f32.shape)
 
 
+# ----------------------------------------------------------------------------------------------- side stream for dW / db
+# Weight and bias gradients are off the backward's critical chain (nothing downstream reads them before the autograd
+# node returns).  With WGRAD_STREAM on they are enqueued on a second CUDA stream, so the tensor-core-bound split-K wgrad
+# GEMMs overlap the chain's HBM-bound kernels (LayerNorm backward, CLS / time attention) and the HBM-bound bias column
+# sums overlap the chain's GEMMs.  Every autograd node joins the side stream before it returns its gradients.
+import contextlib
+import os
+
+WGRAD_STREAM = os.environ.get("LAVILA_B200_WGRAD_STREAM", "0") == "1"
+_SIDE = {}
+
+
+def _side_stream(dev):
+    st = _SIDE.get(dev)
+    if st is None:
+        st = {"stream": torch.cuda.Stream(device=dev), "dirty": False}
+        _SIDE[dev] = st
+    return st
+
+
+@contextlib.contextmanager
+def side_work(*tensors):
+    """Run the enclosed launches on the side stream, ordered after everything already enqueued on the current stream.
+    `tensors` (operands and outputs) are recorded on the side stream so the caching allocator cannot recycle them early."""
+    if not WGRAD_STREAM:
+        yield
+        return
+    dev = tensors[0].device
+    st = _side_stream(dev)
+    main = torch.cuda.current_stream(dev)
+    ev = torch.cuda.Event()
+    ev.record(main)
+    st["stream"].wait_event(ev)
+    with torch.cuda.stream(st["stream"]):
+        yield
+    for t in tensors:
+        if t is not None:
+            t.record_stream(st["stream"])
+    st["dirty"] = True
+
+
+def side_join(dev):
+    """Make the current stream wait for all side-stream work issued so far (no-op if there was none)."""
+    st = _SIDE.get(dev)
+    if st is None or not st["dirty"]:
+        return
+    ev = torch.cuda.Event()
+    ev.record(st["stream"])
+    torch.cuda.current_stream(dev).wait_event(ev)
+    st["dirty"] = False
+
+
 def _zeros_like_param(p):
     return torch.zeros(p.shape, device=p.device, dtype=F32)
 
@@ -109,9 +161,12 @@ def attn_sub_bwd(dy, dy_b, P, S, adds=(), want_bf16=True):
     # ---- proj:  y = resid + gate * (att W^T + b)
     g["proj_w"] = _zeros_like_param(P["proj_w"])
     g["proj_b"] = _zeros_like_param(P["proj_b"])
-    _wgrad(dy_b, S["att"], D, D, M, g["proj_w"])
-    ops.colsum_bf16(dy_b, M, D, g["proj_b"])
+    with side_work(dy_b, S["att"], g["proj_w"], g["proj_b"]):
+        _wgrad(dy_b, S["att"], D, D, M, g["proj_w"])
+        ops.colsum_bf16(dy_b, M, D, g["proj_b"])
     datt = torch.empty(M, D, device=dev, dtype=BF16)
+    if gate is not None:
+        side_join(dev)      # the gate gradient below reads proj_w / proj_b gradients
     if gate is None:
         ops.gemm(dy_b, SHADOW.get(P["proj_w"]), M, D, D, datt, b_mn=1)
     else:
@@ -136,8 +191,9 @@ def attn_sub_bwd(dy, dy_b, P, S, adds=(), want_bf16=True):
     # ---- qkv
     g["qkv_w"] = _zeros_like_param(P["qkv_w"])
     g["qkv_b"] = _zeros_like_param(P["qkv_b"])
-    _wgrad(dqkv, S["ln"], 3 * D, D, M, g["qkv_w"])
-    ops.colsum_bf16(dqkv, M, 3 * D, g["qkv_b"])
+    with side_work(dqkv, S["ln"], g["qkv_w"], g["qkv_b"]):
+        _wgrad(dqkv, S["ln"], 3 * D, D, M, g["qkv_w"])
+        ops.colsum_bf16(dqkv, M, 3 * D, g["qkv_b"])
     dln = torch.empty(M, D, device=dev, dtype=BF16)
     ops.gemm(dqkv, SHADOW.get(P["qkv_w"]), M, D, 3 * D, dln, b_mn=1)
     del dqkv
@@ -177,14 +233,16 @@ def mlp_sub_bwd(dy, dy_b, P, S, want_bf16=True):
     g = {}
     g["fc2_w"] = _zeros_like_param(P["fc2_w"])
     g["fc2_b"] = _zeros_like_param(P["fc2_b"])
-    _wgrad(dy_b, S["act"], D, Hd, M, g["fc2_w"])
-    ops.colsum_bf16(dy_b, M, D, g["fc2_b"])
+    with side_work(dy_b, S["act"], g["fc2_w"], g["fc2_b"]):
+        _wgrad(dy_b, S["act"], D, Hd, M, g["fc2_w"])
+        ops.colsum_bf16(dy_b, M, D, g["fc2_b"])
     dh = torch.empty(M, Hd, device=dev, dtype=BF16)
     ops.gemm(dy_b, SHADOW.get(P["fc2_w"]), M, Hd, D, dh, b_mn=1, flags=L.EPI_DQUICKGELU, aux=S["pre"])
     g["fc1_w"] = _zeros_like_param(P["fc1_w"])
     g["fc1_b"] = _zeros_like_param(P["fc1_b"])
-    _wgrad(dh, S["ln"], Hd, D, M, g["fc1_w"])
-    ops.colsum_bf16(dh, M, Hd, g["fc1_b"])
+    with side_work(dh, S["ln"], g["fc1_w"], g["fc1_b"]):
+        _wgrad(dh, S["ln"], Hd, D, M, g["fc1_w"])
+        ops.colsum_bf16(dh, M, Hd, g["fc1_b"])
     dln = torch.empty(M, D, device=dev, dtype=BF16)
     ops.gemm(dh, SHADOW.get(P["fc1_w"]), M, D, Hd, dln, b_mn=1)
     del dh
@@ -274,6 +332,7 @@ class SpaceTimeBlockFn(torch.autograd.Function):
             "mlp.fc1.bias": g_m["fc1_b"], "mlp.fc2.weight": g_m["fc2_w"], "mlp.fc2.bias": g_m["fc2_b"],
         }
         dgate = g_t.get("gate") if gate is not None else None
+        side_join(dx.device)
         return (dx.view(B, N, D), None, None, None, None, dgate, None) + tuple(grads[k] for k in BLOCK_PARAM_ORDER)
 
 
@@ -367,6 +426,7 @@ class LastBlockClsFn(torch.autograd.Function):
             "mlp.fc1.bias": g_m["fc1_b"], "mlp.fc2.weight": g_m["fc2_w"], "mlp.fc2.bias": g_m["fc2_b"],
         }
         dgate = g_t.get("gate") if gate is not None else None
+        side_join(dx.device)
         return (dx.view(B, N, D), None, None, None, None, dgate) + tuple(grads[k] for k in BLOCK_PARAM_ORDER)
 
 
@@ -414,6 +474,7 @@ class TextBlockFn(torch.autograd.Function):
             "ln_2.weight": g_m["ln_w"], "ln_2.bias": g_m["ln_b"], "mlp.c_fc.weight": g_m["fc1_w"],
             "mlp.c_fc.bias": g_m["fc1_b"], "mlp.c_proj.weight": g_m["fc2_w"], "mlp.c_proj.bias": g_m["fc2_b"],
         }
+        side_join(dx.device)
         return (dx.view(B, Lc, W), None) + tuple(grads[k] for k in TEXT_PARAM_ORDER)
 
 
