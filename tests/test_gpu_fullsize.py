@@ -1,0 +1,83 @@
+"""Size-independent properties at the BASELINE.json configuration itself (CLIP_OPENAI_TIMESFORMER_BASE, 16 frames x 224^2,
+batch 64), where the fp32 oracle is too slow to run: they hold for the reference's math at any size, so a kernel that
+mis-handles the full-size geometry (tile tails, grid limits, 64-bit offsets past 2^31 elements) breaks them.
+  * clip-permutation equivariance of the forward (every row is computed independently: bit exact);
+  * a clip's embedding does not depend on what else is in the batch (batch 64 row == batch 2 row to 1e-6);
+  * backward is linear in the upstream gradient (x2 is exact in binary floating point; split-K atomics -> 1e-5);
+  * CLIPLoss known answers: identical embeddings -> acc 100; swapping the roles of image and text leaves the loss unchanged.
+"""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+B, T = 64, 16
+
+
+@pytest.fixture(scope="module")
+def setup():
+    import contextlib
+    import sys
+    import bench
+    from lavila_b200.models import models as M
+    torch.manual_seed(0)
+    with contextlib.redirect_stdout(sys.stderr):
+        model = M.CLIP_OPENAI_TIMESFORMER_BASE(num_frames=T, project_embed_dim=256)
+    bench.randomise_zero_init(model)
+    model.to(DEV)
+    frames, text = bench.make_batch(B, T, 4321)
+    return model, frames.to(DEV), text.to(DEV)
+
+
+def test_forward_is_permutation_equivariant_and_batch_independent(setup):
+    model, frames, text = setup
+    with torch.no_grad():
+        out = model(frames, text, norm_embed=True)
+        perm = torch.randperm(B, generator=torch.Generator().manual_seed(1)).to(DEV)
+        outp = model(frames[perm].contiguous(), text[perm].contiguous(), norm_embed=True)
+        small = model(frames[62:64].contiguous(), text[62:64].contiguous(), norm_embed=True)
+    assert bool(torch.isfinite(out["image_embed"]).all()) and bool(torch.isfinite(out["text_embed"]).all())
+    assert torch.equal(outp["image_embed"], out["image_embed"][perm])
+    assert torch.equal(outp["text_embed"], out["text_embed"][perm])
+    # the last clips (offsets past 2^31 elements); a 2-clip batch takes the 1-CTA GEMM tiles for its short matrices, so
+    # last-bit differences in the fp32 accumulation are allowed: 1e-6 absolute on unit-norm embeddings
+    assert float((small["image_embed"] - out["image_embed"][62:64]).abs().max()) < 1e-6
+    assert float((small["text_embed"] - out["text_embed"][62:64]).abs().max()) < 1e-6
+    n = out["image_embed"].norm(dim=-1)
+    assert float((n - 1).abs().max()) < 1e-5                                 # F.normalize (models.py:169-170)
+
+
+def test_backward_is_linear_in_upstream_gradient(setup):
+    from lavila_b200.models.loss import CLIPLoss
+    model, frames, text = setup
+    crit = CLIPLoss()
+    names = ["visual.blocks.0.attn.qkv.weight", "visual.blocks.11.mlp.fc2.weight", "visual.blocks.5.timeattn.proj.bias",
+             "visual.pos_embed", "visual.patch_embed.proj.weight", "transformer.resblocks.3.mlp.c_fc.weight",
+             "token_embedding.weight", "logit_scale"]
+    params = dict(model.named_parameters())
+    grads = []
+    for k in (1.0, 2.0):
+        model.zero_grad(set_to_none=True)
+        ld = crit(model(frames, text, norm_embed=True))
+        (k * ld["loss"]).backward()
+        grads.append({n: params[n].grad.clone() for n in names})
+    assert 0.0 < float(ld["loss"]) < 10.0 and 0.0 <= float(ld["clip_acc"]) <= 100.0
+    for n in names:
+        a, b = grads[0][n], grads[1][n]
+        assert bool(torch.isfinite(a).all()) and float(a.abs().max()) > 0, n
+        assert float((2 * a - b).norm() / b.norm()) < 1e-5, n
+
+
+def test_cliploss_known_answers_full_global_batch():
+    """SURVEY 8(c) KATs at the 8-GPU global batch (512 x 256)."""
+    from lavila_b200.models.loss import CLIPLoss
+    g = torch.Generator().manual_seed(2)
+    e = torch.nn.functional.normalize(torch.randn(512, 256, generator=g), dim=-1).to(DEV)
+    t = torch.nn.functional.normalize(torch.randn(512, 256, generator=g), dim=-1).to(DEV)
+    s = torch.tensor(100.0, device=DEV)
+    crit = CLIPLoss()
+    same = crit({"image_embed": e, "text_embed": e, "logit_scale": s})
+    assert float(same["clip_acc"]) == 100.0 and float(same["loss"]) < 1e-3
+    ab = crit({"image_embed": e, "text_embed": t, "logit_scale": s})
+    ba = crit({"image_embed": t, "text_embed": e, "logit_scale": s})
+    assert abs(float(ab["loss"]) - float(ba["loss"])) < 1e-5 * float(ab["loss"])

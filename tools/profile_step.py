@@ -20,17 +20,19 @@ def main():
     ap.add_argument("--frames", type=int, default=16)
     ap.add_argument("--warmup", type=int, default=2)
     ap.add_argument("--range", default="step", choices=["step", "fwd", "bwd"])
+    ap.add_argument("--model", default="base", choices=list(bench.MODELS))
     a = ap.parse_args()
     from lavila_b200.models import models as M
     from lavila_b200.models.loss import CLIPLoss
     dev = torch.device("cuda", 0)
     torch.manual_seed(0)
-    model = M.CLIP_OPENAI_TIMESFORMER_BASE(num_frames=a.frames, project_embed_dim=256)
+    factory, img_size, _ = bench.MODELS[a.model]
+    model = getattr(M, factory)(num_frames=a.frames, project_embed_dim=256)
     bench.randomise_zero_init(model)
     model.to(dev)
     crit = CLIPLoss(use_vissl=True, rank=0, world_size=1)
     opt = torch.optim.AdamW(bench.param_groups(model), lr=3e-5, weight_decay=0.01)
-    fr, tx = bench.make_batch(a.batch, a.frames, 1234)
+    fr, tx = bench.make_batch(a.batch, a.frames, 1234, img_size)
     fr, tx = fr.to(dev), tx.to(dev)
     rt = torch.cuda.cudart()
 
