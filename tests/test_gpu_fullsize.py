@@ -2,7 +2,7 @@
 batch 64), where the fp32 oracle is too slow to run: they hold for the reference's math at any size, so a kernel that
 mis-handles the full-size geometry (tile tails, grid limits, 64-bit offsets past 2^31 elements) breaks them.
   * clip-permutation equivariance of the forward (every row is computed independently: bit exact);
-  * a clip's embedding does not depend on what else is in the batch (batch 64 row == batch 2 row to 1e-6);
+  * a clip's embedding does not depend on what else is in the batch (batch 64 row == batch 4 row to 1e-6);
   * backward is linear in the upstream gradient (x2 is exact in binary floating point; split-K atomics -> 1e-5);
   * CLIPLoss known answers: identical embeddings -> acc 100; swapping the roles of image and text leaves the loss unchanged.
 """
@@ -35,14 +35,13 @@ def test_forward_is_permutation_equivariant_and_batch_independent(setup):
         out = model(frames, text, norm_embed=True)
         perm = torch.randperm(B, generator=torch.Generator().manual_seed(1)).to(DEV)
         outp = model(frames[perm].contiguous(), text[perm].contiguous(), norm_embed=True)
-        small = model(frames[62:64].contiguous(), text[62:64].contiguous(), norm_embed=True)
+        small = model(frames[60:64].contiguous(), text[60:64].contiguous(), norm_embed=True)
     assert bool(torch.isfinite(out["image_embed"]).all()) and bool(torch.isfinite(out["text_embed"]).all())
     assert torch.equal(outp["image_embed"], out["image_embed"][perm])
     assert torch.equal(outp["text_embed"], out["text_embed"][perm])
-    # the last clips (offsets past 2^31 elements); a 2-clip batch takes the 1-CTA GEMM tiles for its short matrices, so
-    # last-bit differences in the fp32 accumulation are allowed: 1e-6 absolute on unit-norm embeddings
-    assert float((small["image_embed"] - out["image_embed"][62:64]).abs().max()) < 1e-6
-    assert float((small["text_embed"] - out["text_embed"][62:64]).abs().max()) < 1e-6
+    # the last clips (offsets past 2^31 elements) alone, 4 of them so that every GEMM takes the same tile kernel as at 64
+    assert float((small["image_embed"] - out["image_embed"][60:64]).abs().max()) < 1e-6
+    assert float((small["text_embed"] - out["text_embed"][60:64]).abs().max()) < 1e-6
     n = out["image_embed"].norm(dim=-1)
     assert float((n - 1).abs().max()) < 1e-5                                 # F.normalize (models.py:169-170)
 
