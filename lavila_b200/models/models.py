@@ -84,6 +84,89 @@ class CLIP(nn.Module):
         return {'image_embed': image_embed, 'text_embed': text_embed, 'logit_scale': self.logit_scale.exp()}
 
 
+class CLIP_HF(nn.Module):
+    """models.py:176-290: dual encoder whose text tower is a Hugging Face module (DistilBERT in the TSF-L@HR recipe,
+    docs/PRETRAIN.md:24-36).  The video tower, both projections, the normalisation and the loss run on the B200 kernels;
+    the HF text module (0.8 % of the step's FLOPs) is called as it is -- library code, like the reference does -- and its
+    output joins the kernel path through ordinary autograd."""
+
+    def __init__(self, embed_dim: int, vision_width: int, vision_model: nn.Module, text_width: int, text_model: nn.Module,
+                 text_use_cls_token: bool, text_is_regressive: bool, tempearture_init=0.07, **kwargs):
+        super().__init__()
+        self.vision_width = vision_width
+        self.visual = vision_model
+        self.text_width = text_width
+        self.textual = text_model
+        self.text_use_cls_token = text_use_cls_token
+        self.text_is_regressive = text_is_regressive
+        self.projection = kwargs.get('projection', 'default')
+        if self.projection == 'default':
+            self.image_projection = nn.Parameter(torch.empty(vision_width, embed_dim))
+            self.text_projection = nn.Parameter(torch.empty(text_width, embed_dim))
+        elif self.projection == 'frozen_in_time':
+            self.image_projection = nn.Sequential(nn.Linear(vision_width, embed_dim))
+            self.text_projection = nn.Sequential(nn.ReLU(), nn.Linear(text_width, embed_dim))
+        else:
+            raise NotImplementedError(self.projection)
+        print("=> initialize initial temperature with {}".format(tempearture_init))
+        self.logit_scale = nn.Parameter(torch.ones([]) * np.log(1 / tempearture_init))
+        self.initialize_parameters()
+
+    def initialize_parameters(self):
+        """models.py:219-225."""
+        if self.projection == 'default':
+            nn.init.normal_(self.image_projection, std=self.vision_width ** -0.5)
+            nn.init.normal_(self.text_projection, std=self.text_width ** -0.5)
+        else:
+            nn.init.normal_(self.image_projection[0].weight, std=self.vision_width ** -0.5)
+            nn.init.normal_(self.text_projection[1].weight, std=self.text_width ** -0.5)
+
+    @staticmethod
+    def _linear(x, lin):
+        """The 'frozen_in_time' projection heads (EgoVLP, models.py:660-688): [B, K] x [K, N] on B rows -- plain library call."""
+        return torch.nn.functional.linear(x, lin.weight, lin.bias)
+
+    def encode_image(self, image, use_checkpoint=False, apply_project=True):
+        x = self.visual(image, use_checkpoint=use_checkpoint)
+        if isinstance(x, list):
+            assert len(x) == 1
+            x = x[0]
+        if not apply_project:
+            return x
+        if self.projection == 'default':
+            return E.ProjectFn.apply(x, self.image_projection)
+        return self._linear(x, self.image_projection[0])
+
+    def encode_text(self, text, attention_mask=None, use_checkpoint=False):
+        """models.py:249-280 (the gradient-checkpointing toggles are forwarded when the HF module has them)."""
+        toggle = getattr(self.textual, 'gradient_checkpointing_enable' if use_checkpoint else 'gradient_checkpointing_disable', None)
+        if toggle is not None and not (use_checkpoint and type(self.textual).__name__ == 'DistilBertModel'):
+            try:
+                toggle()
+            except Exception:
+                pass
+        x = self.textual(text, attention_mask=attention_mask)
+        if self.text_is_regressive:
+            x = x.last_hidden_state
+            x = x[torch.arange(x.shape[0], device=x.device), text.argmax(dim=-1)]
+        elif self.text_use_cls_token:
+            x = x.last_hidden_state[:, 0, :]
+        else:
+            x = x.pooler_output
+        x = x.float().contiguous()
+        if self.projection == 'default':
+            return E.ProjectFn.apply(x, self.text_projection)
+        return self._linear(torch.relu(x), self.text_projection[1])
+
+    def forward(self, image, text, mask=None, use_checkpoint=False, norm_embed=False):
+        image_embed = self.encode_image(image, use_checkpoint=use_checkpoint)
+        text_embed = self.encode_text(text, attention_mask=mask, use_checkpoint=use_checkpoint)
+        if norm_embed:
+            image_embed = E.L2NormalizeFn.apply(image_embed)
+            text_embed = E.L2NormalizeFn.apply(text_embed)
+        return {'image_embed': image_embed, 'text_embed': text_embed, 'logit_scale': self.logit_scale.exp()}
+
+
 def get_loss(model, args, tokenizer=None):
     """models.py:293-304 (CLIP branch)."""
     if model.startswith('CLIP'):
@@ -222,3 +305,52 @@ def VCLM_OPENAI_TIMESFORMER_LARGE_336PX_GPT2_XL(gated_xattn=False, random_init_g
     """models.py:1138-1198: TSF-L/14 336px (576 patches per frame) + GPT-2 XL, cross-attention every 3rd layer."""
     return _vclm(dict(_TSF_L_336), 1024, dict(n_embd=1600, n_layer=48, n_head=25), 3, 25, num_frames, gated_xattn,
                  timesformer_gated_xattn, freeze_lm_vclm, freeze_visual_vclm, freeze_visual_vclm_temporal, checkpoint, kwargs)
+
+
+# ------------------------------------------------------------------------------------------------ CLIP_HF factories
+def _build_hf(vision_kwargs, num_frames, timesformer_gated_xattn, drop_path_rate, timesformer_freeze_space, temperature_init,
+              project_embed_dim, text_model, checkpoint, kwargs):
+    vision_model = SpaceTimeTransformer(num_frames=num_frames, time_init='zeros', attention_style='frozen-in-time',
+                                        ln_pre=True, act_layer=QuickGELU, is_tanh_gating=timesformer_gated_xattn,
+                                        drop_path_rate=drop_path_rate, **vision_kwargs)
+    vision_model.head = nn.Identity()
+    vision_model.pre_logits = nn.Identity()
+    vision_model.fc = nn.Identity()
+    if text_model is None:
+        from transformers import DistilBertConfig, DistilBertModel
+        print("=> no network: DistilBERT-base is randomly initialised (reference loads 'distilbert-base-uncased')")
+        text_model = DistilBertModel(DistilBertConfig())
+    kwargs.pop('text_use_cls_token', None)   # models.py:533: DistilBERT has no pooler, the CLS token is always used
+    model = CLIP_HF(embed_dim=project_embed_dim, vision_width=vision_model.embed_dim, vision_model=vision_model,
+                    text_width=text_model.config.hidden_size, text_model=text_model, text_use_cls_token=True,
+                    text_is_regressive=False, tempearture_init=temperature_init, **kwargs)
+    _load_checkpoint(model, checkpoint)
+    if timesformer_freeze_space:
+        for n, p in vision_model.named_parameters():
+            p.requires_grad = ('temporal_embed' in n or 'timeattn' in n or 'norm3' in n or n == 'cls_token'
+                               or 'alpha_timeattn' in n)
+    return model
+
+
+def CLIP_OPENAI_TIMESFORMER_BASE_DISTILBERT_BASE(num_frames=4, timesformer_gated_xattn=False, drop_path_rate=0,
+                                                 timesformer_freeze_space=False, temperature_init=0.07, project_embed_dim=256,
+                                                 text_model=None, checkpoint=None, **kwargs):
+    """models.py:494-545: TSF-B/16 + DistilBERT-base text tower (CLS token)."""
+    return _build_hf({}, num_frames, timesformer_gated_xattn, drop_path_rate, timesformer_freeze_space, temperature_init,
+                     project_embed_dim, text_model, checkpoint, kwargs)
+
+
+def CLIP_OPENAI_TIMESFORMER_LARGE_DISTILBERT_BASE(num_frames=4, timesformer_gated_xattn=False, drop_path_rate=0,
+                                                  timesformer_freeze_space=False, temperature_init=0.07, project_embed_dim=256,
+                                                  text_model=None, checkpoint=None, **kwargs):
+    """models.py:548-601: TSF-L/14 224px + DistilBERT-base."""
+    return _build_hf(dict(_TSF_L), num_frames, timesformer_gated_xattn, drop_path_rate, timesformer_freeze_space,
+                     temperature_init, project_embed_dim, text_model, checkpoint, kwargs)
+
+
+def CLIP_OPENAI_TIMESFORMER_LARGE_336PX_DISTILBERT_BASE(num_frames=4, timesformer_gated_xattn=False, drop_path_rate=0,
+                                                        timesformer_freeze_space=False, temperature_init=0.07,
+                                                        project_embed_dim=256, text_model=None, checkpoint=None, **kwargs):
+    """models.py:604-657: TSF-L/14 336px + DistilBERT-base (the TSF-L@HR recipe, docs/PRETRAIN.md:24-36)."""
+    return _build_hf(dict(_TSF_L_336), num_frames, timesformer_gated_xattn, drop_path_rate, timesformer_freeze_space,
+                     temperature_init, project_embed_dim, text_model, checkpoint, kwargs)

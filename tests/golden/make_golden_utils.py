@@ -44,6 +44,20 @@ def main():
     rem = remap_keys({k: v.clone() for k, v in sd.items()}, transformer_layers=2)
     out["remap"] = {"layers": 2, "width": 8, "keys": list(rem.keys()), "shapes": {k: tuple(v.shape) for k, v in rem.items()},
                     "checksums": {k: float(v.double().sum()) for k, v in rem.items()}}
+    # state_dict contract of the reference CLIP_HF + DistilBERT (models.py:176-290) at toy size
+    import torch.nn as nn
+    from transformers import DistilBertConfig, DistilBertModel
+    from lavila.models.models import CLIP_HF
+    from lavila.models.openai_model import QuickGELU
+    from lavila.models.timesformer import SpaceTimeTransformer
+    vis = SpaceTimeTransformer(img_size=32, patch_size=16, embed_dim=64, depth=1, num_heads=1, num_frames=2, time_init='zeros',
+                               attention_style='frozen-in-time', ln_pre=True, act_layer=QuickGELU)
+    vis.head = vis.pre_logits = vis.fc = nn.Identity()
+    ref = CLIP_HF(embed_dim=16, vision_width=64, vision_model=vis, text_width=32,
+                  text_model=DistilBertModel(DistilBertConfig(vocab_size=100, dim=32, n_layers=1, n_heads=2, hidden_dim=64,
+                                                              max_position_embeddings=16)),
+                  text_use_cls_token=True, text_is_regressive=False)
+    out["clip_hf_state"] = {k: tuple(v.shape) for k, v in ref.state_dict().items()}
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "utils_small.pt")
     torch.save(out, path)
     print("wrote", path, os.path.getsize(path), "bytes")

@@ -180,3 +180,58 @@ def test_use_checkpoint_recompute_matches():
     assert res[0][1].keys() == res[1][1].keys()
     for k in res[0][1]:
         assert rel_l2(res[1][1][k], res[0][1][k]) < 1e-5, k
+
+
+def test_clip_hf_distilbert_vs_oracle():
+    """CLIP_HF (models.py:176-290): TimeSformer tower + projections + normalise + loss on the kernels, DistilBERT text tower
+    through the HF module.  Reference math = oracle TimeSformer, the same HF module in fp32, `x[:, 0] @ text_projection`."""
+    from transformers import DistilBertConfig, DistilBertModel
+    from lavila_b200.models.models import CLIP_HF
+    from lavila_b200.models.loss import CLIPLoss
+    from lavila_b200.models.timesformer import SpaceTimeTransformer, QuickGELU
+    cfg = GOLD["norm"]["cfg"]
+    params = O.init_params(cfg, seed=21)
+    torch.manual_seed(0)
+    bert = DistilBertModel(DistilBertConfig(vocab_size=200, dim=128, n_layers=2, n_heads=2, hidden_dim=256,
+                                            max_position_embeddings=32, dropout=0.0, attention_dropout=0.0)).to(DEV).eval()
+    vis = SpaceTimeTransformer(img_size=cfg["img_size"], patch_size=cfg["patch_size"], embed_dim=cfg["embed_dim"],
+                               depth=cfg["depth"], num_heads=cfg["num_heads"], num_frames=cfg["num_frames"], time_init="zeros",
+                               ln_pre=True, act_layer=QuickGELU)
+    vis.head = torch.nn.Identity()
+    vis.pre_logits = torch.nn.Identity()
+    m = CLIP_HF(embed_dim=cfg["project_dim"], vision_width=cfg["embed_dim"], vision_model=vis, text_width=128, text_model=bert,
+                text_use_cls_token=True, text_is_regressive=False)
+    vsd = {k[len("visual."):]: v for k, v in params.items() if k.startswith("visual.")}
+    assert not m.visual.load_state_dict(vsd, strict=False).unexpected_keys
+    with torch.no_grad():
+        m.image_projection.copy_(params["image_projection"])
+    m.to(DEV)
+    B = 4
+    frames, _ = O.synthetic_batch(cfg, B, seed=5)
+    g = torch.Generator().manual_seed(6)
+    ids = torch.randint(1, 200, (B, 12), generator=g)
+    mask = torch.ones(B, 12, dtype=torch.int64)
+    mask[1, 8:] = 0
+    mask[3, 5:] = 0
+    frames, ids, mask = frames.to(DEV), ids.to(DEV), mask.to(DEV)
+    out = m(frames, ids, mask=mask, norm_embed=True)
+    ld = CLIPLoss()(out)
+    ld["loss"].backward()
+    g_tp = m.text_projection.grad.clone()
+    g_emb = m.textual.embeddings.word_embeddings.weight.grad.clone()
+    g_qkv = m.visual.blocks[0].attn.qkv.weight.grad.clone()
+    # reference
+    m.zero_grad(set_to_none=True)
+    pr = {k: v.to(DEV).requires_grad_(True) for k, v in params.items() if k.startswith("visual.") or k == "image_projection"}
+    tp = m.text_projection.detach().clone().requires_grad_(True)
+    img = O.encode_image(frames, pr, cfg)
+    txt = bert(ids, attention_mask=mask).last_hidden_state[:, 0] @ tp
+    img, txt = torch.nn.functional.normalize(img, dim=-1), torch.nn.functional.normalize(txt, dim=-1)
+    rl = O.clip_loss(img, txt, m.logit_scale.detach().exp())
+    rl["loss"].backward()
+    assert_close_bf16(out["image_embed"], img, "CLIP_HF image_embed")
+    assert_close_bf16(out["text_embed"], txt, "CLIP_HF text_embed")
+    assert abs(float(ld["loss"]) - float(rl["loss"])) < 3e-2
+    assert_close_bf16(g_tp, tp.grad, "d text_projection", rel=6e-2, cos=0.99)
+    assert_close_bf16(g_emb, m.textual.embeddings.word_embeddings.weight.grad, "d DistilBERT word embeddings", rel=6e-2, cos=0.99)
+    assert_close_bf16(g_qkv, pr["visual.blocks.0.attn.qkv.weight"].grad, "d visual qkv", rel=6e-2, cos=0.99)

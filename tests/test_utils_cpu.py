@@ -44,3 +44,20 @@ def test_rsetattr_rgetattr():
     U.rsetattr(m, "0.weight.data", torch.ones(2, 2))
     assert float(U.rgetattr(m, "0.weight").sum()) == 4.0
     assert U.rgetattr(m, "0.missing", None) is None
+
+
+def test_clip_hf_state_dict_contract():
+    """Our CLIP_HF + the HF DistilBERT module exposes exactly the reference's state_dict keys and shapes."""
+    import torch.nn as nn
+    from transformers import DistilBertConfig, DistilBertModel
+    from lavila_b200.models.models import CLIP_HF
+    from lavila_b200.models.timesformer import SpaceTimeTransformer, QuickGELU
+    vis = SpaceTimeTransformer(img_size=32, patch_size=16, embed_dim=64, depth=1, num_heads=1, num_frames=2, time_init='zeros',
+                               ln_pre=True, act_layer=QuickGELU)
+    vis.head = nn.Identity()
+    vis.pre_logits = nn.Identity()
+    m = CLIP_HF(embed_dim=16, vision_width=64, vision_model=vis, text_width=32,
+                text_model=DistilBertModel(DistilBertConfig(vocab_size=100, dim=32, n_layers=1, n_heads=2, hidden_dim=64,
+                                                            max_position_embeddings=16)),
+                text_use_cls_token=True, text_is_regressive=False)
+    assert {k: tuple(v.shape) for k, v in m.state_dict().items()} == G["clip_hf_state"]
