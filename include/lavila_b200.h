@@ -132,6 +132,11 @@ int lv_space_attn_bwd_tc(const void* qkv, int64_t ld_qkv, const void* out, int64
 int lv_flash_attn_fwd(const void* q, int64_t ld_q, int64_t q_rows, const void* k, const void* v, int64_t ld_kv,
                       int64_t kv_rows, int kv_head_stride, void* out, int64_t ld_out, int B, int H, int Lq, int Lk,
                       int causal, float scale, void* stream);
+/* Same, but the key count Lk is read from device memory (*lk_dev, 1 <= *lk_dev <= kv_rows) at run time: one captured
+ * CUDA graph of a KV-cached decoding step (gpt2_gated.py:331-345 `layer_past`) can be replayed for every position. */
+int lv_flash_attn_fwd_dyn(const void* q, int64_t ld_q, int64_t q_rows, const void* k, const void* v, int64_t ld_kv,
+                          int64_t kv_rows, int kv_head_stride, void* out, int64_t ld_out, int B, int H, int Lq,
+                          const int32_t* lk_dev, int causal, float scale, void* stream);
 /* Debug: device buffer (>= 256 int64) receiving clock64() phase stamps of CTA 0 of lv_space_attn_bwd_tc; NULL disables. */
 int lv_debug_set_buffer(void* buf);
 int lv_cls_attn_fwd(const void* qkv, int64_t ld_qkv, void* out, int64_t ld_out, float* lse, int B, int H, int N,

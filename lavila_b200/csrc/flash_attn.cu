@@ -25,6 +25,7 @@ struct Params {
   int kv_head_stride;
   int Lq, Lk, causal;
   float scale;
+  const int* lk_ptr;   // optional: the key count lives in device memory (CUDA-graph replay of a decoding step)
 };
 
 __device__ __forceinline__ uint32_t swz(int row, int chunk) { return row * ROW_BYTES + ((chunk ^ (row & 7)) << 4); }
@@ -64,8 +65,9 @@ flash_fwd_kernel(const Params p) {
   const __nv_bfloat16* kbase = p.k + (long long)b * p.kv_rows * p.ld_kv + h * p.kv_head_stride;
   const __nv_bfloat16* vbase = p.v + (long long)b * p.kv_rows * p.ld_kv + h * p.kv_head_stride;
   const int nq = min(BQ, p.Lq - q0);
-  int Lk_eff = p.Lk;   // causal: keys beyond the last query row of this block are never visible
-  if (p.causal) Lk_eff = min(p.Lk, q0 + nq + (p.Lk - p.Lq));
+  const int Lk = p.lk_ptr ? __ldg(p.lk_ptr) : p.Lk;
+  int Lk_eff = Lk;   // causal: keys beyond the last query row of this block are never visible
+  if (p.causal) Lk_eff = min(Lk, q0 + nq + (Lk - p.Lq));
   const int nblocks = (Lk_eff + BK - 1) / BK;
 
   load_rows(sQ, qbase, p.ld_q, q0, nq, tid);
@@ -75,7 +77,7 @@ flash_fwd_kernel(const Params p) {
 
   const int g = lane >> 2, t = lane & 3;
   const int r0 = warp * 16 + g, r1 = r0 + 8;          // rows inside the query block
-  const int off = p.Lk - p.Lq;
+  const int off = Lk - p.Lq;
   const float sl2 = p.scale * LOG2E;
   float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
   float o[8][4];
@@ -119,7 +121,7 @@ flash_fwd_kernel(const Params p) {
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         const int col = k0 + nt * 8 + 2 * t + e;
-        const bool in = col < p.Lk;
+        const bool in = col < Lk;
         const bool v0 = in && (!p.causal || col <= q0 + r0 + off), v1 = in && (!p.causal || col <= q0 + r1 + off);
         s[nt][e] = v0 ? s[nt][e] : -INFINITY;
         s[nt][2 + e] = v1 ? s[nt][2 + e] : -INFINITY;
@@ -187,17 +189,32 @@ flash_fwd_kernel(const Params p) {
 
 using namespace lv;
 
-extern "C" int lv_flash_attn_fwd(const void* q, int64_t ld_q, int64_t q_rows, const void* k, const void* v, int64_t ld_kv,
-                                 int64_t kv_rows, int kv_head_stride, void* out, int64_t ld_out, int B, int H, int Lq, int Lk,
-                                 int causal, float scale, void* stream) {
-  LV_REQUIRE(q && k && v && out && B > 0 && H > 0 && Lq > 0 && Lk > 0, "lv_flash_attn_fwd: bad arguments");
-  LV_REQUIRE(ld_q % 8 == 0 && ld_kv % 8 == 0 && ld_out % 8 == 0 && kv_head_stride % 8 == 0, "lv_flash_attn_fwd: strides must be multiples of 8 elements");
-  LV_REQUIRE(((uintptr_t)q & 15) == 0 && ((uintptr_t)k & 15) == 0 && ((uintptr_t)v & 15) == 0 && ((uintptr_t)out & 15) == 0, "lv_flash_attn_fwd: pointers must be 16-byte aligned");
+static int flash_launch(const void* q, int64_t ld_q, int64_t q_rows, const void* k, const void* v, int64_t ld_kv, int64_t kv_rows,
+                        int kv_head_stride, void* out, int64_t ld_out, int B, int H, int Lq, int Lk, const int32_t* lk_dev,
+                        int causal, float scale, void* stream, const char* what) {
+  LV_REQUIRE(q && k && v && out && B > 0 && H > 0 && Lq > 0 && (Lk > 0 || lk_dev), "%s: bad arguments", what);
+  LV_REQUIRE(ld_q % 8 == 0 && ld_kv % 8 == 0 && ld_out % 8 == 0 && kv_head_stride % 8 == 0, "%s: strides must be multiples of 8 elements", what);
+  LV_REQUIRE(((uintptr_t)q & 15) == 0 && ((uintptr_t)k & 15) == 0 && ((uintptr_t)v & 15) == 0 && ((uintptr_t)out & 15) == 0, "%s: pointers must be 16-byte aligned", what);
   flash::Params p{};
   p.q = (const __nv_bfloat16*)q; p.k = (const __nv_bfloat16*)k; p.v = (const __nv_bfloat16*)v; p.out = (__nv_bfloat16*)out;
   p.ld_q = ld_q; p.ld_kv = ld_kv; p.ld_out = ld_out; p.q_rows = q_rows; p.kv_rows = kv_rows;
-  p.kv_head_stride = kv_head_stride; p.Lq = Lq; p.Lk = Lk; p.causal = causal; p.scale = scale;
+  p.kv_head_stride = kv_head_stride; p.Lq = Lq; p.Lk = Lk; p.causal = causal; p.scale = scale; p.lk_ptr = lk_dev;
   dim3 grid((Lq + flash::BQ - 1) / flash::BQ, H, B);
   flash::flash_fwd_kernel<<<grid, flash::WARPS * 32, 0, (cudaStream_t)stream>>>(p);
-  return check_launch("lv_flash_attn_fwd");
+  return check_launch(what);
+}
+
+extern "C" int lv_flash_attn_fwd(const void* q, int64_t ld_q, int64_t q_rows, const void* k, const void* v, int64_t ld_kv,
+                                 int64_t kv_rows, int kv_head_stride, void* out, int64_t ld_out, int B, int H, int Lq, int Lk,
+                                 int causal, float scale, void* stream) {
+  return flash_launch(q, ld_q, q_rows, k, v, ld_kv, kv_rows, kv_head_stride, out, ld_out, B, H, Lq, Lk, nullptr, causal, scale,
+                      stream, "lv_flash_attn_fwd");
+}
+
+extern "C" int lv_flash_attn_fwd_dyn(const void* q, int64_t ld_q, int64_t q_rows, const void* k, const void* v, int64_t ld_kv,
+                                     int64_t kv_rows, int kv_head_stride, void* out, int64_t ld_out, int B, int H, int Lq,
+                                     const int32_t* lk_dev, int causal, float scale, void* stream) {
+  LV_REQUIRE(lk_dev, "lv_flash_attn_fwd_dyn: lk_dev is NULL");
+  return flash_launch(q, ld_q, q_rows, k, v, ld_kv, kv_rows, kv_head_stride, out, ld_out, B, H, Lq, 0, lk_dev, causal, scale,
+                      stream, "lv_flash_attn_fwd_dyn");
 }

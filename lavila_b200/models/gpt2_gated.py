@@ -133,24 +133,31 @@ class GPT2Block(nn.Module):
         _linear(a, mlp.c_proj, M, out, flags=fl, resid=h, scale=gate)
         return out
 
-    def forward_rows(self, h, B, Lq, ctx_kv_cache, ctx_bf16, ctx_rows, self_kv_cache=None, past_len=0):
+    def forward_rows(self, h, B, Lq, ctx_kv_cache, ctx_bf16, ctx_rows, self_kv_cache=None, past_len=0, dyn=None):
         """h: fp32 [B*Lq, H] residual stream.  ctx_bf16: bf16 [B*ctx_rows, H] (already cast) or None.
         self_kv_cache (dict with "max_len", filled per layer) + past_len: incremental decoding -- the rows are positions
         past_len .. past_len+Lq-1, their keys/values are appended to the layer's cache and attention runs over the
-        past_len+Lq cached keys (same numbers as re-running the whole prefix, gpt2_gated.py:331-345 `layer_past`)."""
+        past_len+Lq cached keys (same numbers as re-running the whole prefix, gpt2_gated.py:331-345 `layer_past`).
+        dyn (dict: "pos_idx" int64[1], "lk_dev" int32[1] on the device): the position lives in device memory, so that ONE
+        captured CUDA graph of this step can be replayed for every position (Lq must be 1; every launch has static arguments)."""
         M, H = h.shape
         heads = self.attn.num_heads
         dev = h.device
-        if ctx_bf16 is not None and hasattr(self, "crossattention"):
+        if ctx_rows > 0 and hasattr(self, "crossattention"):
             ca = self.crossattention
             y = self._ln(h, self.ln_cross_attn, M, H)
             q = torch.empty(M, H, device=dev, dtype=BF16)
             _linear(y, ca.q_attn, M, q)
             kv = ctx_kv_cache.get(self.layer_idx)
-            if kv is None:   # K/V of the video tokens are projected once per clip, not once per decoding step
-                kv = torch.empty(ctx_bf16.shape[0], 2 * H, device=dev, dtype=BF16)
-                _linear(ctx_bf16, ca.c_attn, ctx_bf16.shape[0], kv)
-                ctx_kv_cache[self.layer_idx] = kv
+            stale = ctx_kv_cache.get("_stale")    # layers whose (persistent) K/V buffer belongs to a previous batch of clips
+            if kv is None or (stale is not None and self.layer_idx in stale):
+                # K/V of the video tokens are projected once per clip, not once per decoding step
+                if kv is None:
+                    kv = torch.empty(B * ctx_rows, 2 * H, device=dev, dtype=BF16)
+                    ctx_kv_cache[self.layer_idx] = kv
+                _linear(ctx_bf16, ca.c_attn, B * ctx_rows, kv)
+                if stale is not None:
+                    stale.discard(self.layer_idx)
             att = torch.empty(M, H, device=dev, dtype=BF16)
             ops.flash_attn_fwd(q, kv, kv[:, H:], att, B, heads, Lq, ctx_rows, q_rows=Lq, kv_rows=ctx_rows, ld_q=H,
                                ld_kv=2 * H, ld_out=H, causal=False)
@@ -174,10 +181,15 @@ class GPT2Block(nn.Module):
             if kv is None:
                 kv = torch.zeros(B, Lmax, 2 * H, device=dev, dtype=BF16)
                 self_kv_cache[self.layer_idx] = kv
-            kv[:, past_len:past_len + Lq].copy_(qkv.view(B, Lq, 3 * H)[:, :, H:])
             kv2 = kv.view(B * Lmax, 2 * H)
-            ops.flash_attn_fwd(qkv, kv2, kv2[:, H:], att, B, heads, Lq, past_len + Lq, q_rows=Lq, kv_rows=Lmax, ld_q=3 * H,
-                               ld_kv=2 * H, ld_out=H, causal=True)
+            if dyn is None:
+                kv[:, past_len:past_len + Lq].copy_(qkv.view(B, Lq, 3 * H)[:, :, H:])
+                ops.flash_attn_fwd(qkv, kv2, kv2[:, H:], att, B, heads, Lq, past_len + Lq, q_rows=Lq, kv_rows=Lmax,
+                                   ld_q=3 * H, ld_kv=2 * H, ld_out=H, causal=True)
+            else:
+                kv.index_copy_(1, dyn["pos_idx"], qkv.view(B, 1, 3 * H)[:, :, H:])
+                ops.flash_attn_fwd_dyn(qkv, kv2, kv2[:, H:], att, B, heads, 1, dyn["lk_dev"], q_rows=1, kv_rows=Lmax,
+                                       ld_q=3 * H, ld_kv=2 * H, ld_out=H, causal=True)
         h2 = torch.empty(M, H, device=dev, dtype=F32)
         _linear(att, self.attn.c_proj, M, h2, flags=L.EPI_RESID, resid=h)
         return self._ffn(h2, self.ln_2, self.mlp, M, H, L.EPI_GELU_TANH, None)
@@ -196,21 +208,28 @@ class GPT2Model(nn.Module):
         self.ln_f = nn.LayerNorm(self.embed_dim, eps=getattr(config, "layer_norm_epsilon", 1e-5))
 
     @torch.no_grad()
-    def forward_rows(self, input_ids, encoder_hidden_states=None, ctx_kv_cache=None, self_kv_cache=None, past_len=0):
+    def forward_rows(self, input_ids, encoder_hidden_states=None, ctx_kv_cache=None, self_kv_cache=None, past_len=0, dyn=None):
         B, Lq = input_ids.shape
         H = self.embed_dim
         dev = self.wte.weight.device
-        h = torch.empty(B * Lq, H, device=dev, dtype=F32)
-        # positions past_len .. past_len+Lq-1 (gpt2_gated.py:855-858 position_ids with past_length)
-        ops.text_embed(input_ids.contiguous(), self.wte.weight, self.wpe.weight[past_len:], h, B * Lq, Lq, H,
-                       self.wte.weight.shape[0])
-        ctx_b, ctx_rows = None, 0
-        if encoder_hidden_states is not None:
-            ctx_rows = encoder_hidden_states.shape[1]
-            ctx_b = ops.cast_bf16(encoder_hidden_states.contiguous().float().view(-1, H))
         cache = ctx_kv_cache if ctx_kv_cache is not None else {}
+        ctx_b, ctx_rows = None, 0
+        if dyn is None:
+            h = torch.empty(B * Lq, H, device=dev, dtype=F32)
+            # positions past_len .. past_len+Lq-1 (gpt2_gated.py:855-858 position_ids with past_length)
+            ops.text_embed(input_ids.contiguous(), self.wte.weight, self.wpe.weight[past_len:], h, B * Lq, Lq, H,
+                           self.wte.weight.shape[0])
+            if encoder_hidden_states is not None:
+                ctx_rows = encoder_hidden_states.shape[1]
+                ctx_b = ops.cast_bf16(encoder_hidden_states.contiguous().float().view(-1, H))
+        else:
+            # graph-replayable step: the position is a device scalar, the cross-attention K/V are already cached
+            assert Lq == 1 and self_kv_cache is not None
+            h = self.wte.weight[input_ids.reshape(-1)] + self.wpe.weight[dyn["pos_idx"]]
+            if encoder_hidden_states is not None:
+                ctx_rows = encoder_hidden_states.shape[1]
         for blk in self.h:
-            h = blk.forward_rows(h, B, Lq, cache, ctx_b, ctx_rows, self_kv_cache, past_len)
+            h = blk.forward_rows(h, B, Lq, cache, ctx_b, ctx_rows, self_kv_cache, past_len, dyn)
         y = torch.empty(B * Lq, H, device=dev, dtype=BF16)
         ops.layernorm_fwd(h, self.ln_f.weight, self.ln_f.bias, self.ln_f.eps, B * Lq, H, y_bf16=y)
         return y
@@ -259,12 +278,12 @@ class GPT2LMHeadModel(nn.Module):
 
     @torch.no_grad()
     def forward(self, input_ids=None, encoder_hidden_states=None, last_only=False, ctx_kv_cache=None, self_kv_cache=None,
-                past_len=0, **kwargs):
+                past_len=0, dyn=None, **kwargs):
         """Returns an object with `.logits` [B, L, vocab] fp32 (or [B, 1, vocab] with last_only=True).
         With self_kv_cache, input_ids holds only the NEW positions past_len .. past_len+L-1."""
         B, Lq = input_ids.shape
         H = self.transformer.embed_dim
-        y = self.transformer.forward_rows(input_ids, encoder_hidden_states, ctx_kv_cache, self_kv_cache, past_len)
+        y = self.transformer.forward_rows(input_ids, encoder_hidden_states, ctx_kv_cache, self_kv_cache, past_len, dyn)
         wb, V, Vp = self._padded_head()
         if last_only:
             y = y.view(B, Lq, H)[:, -1].contiguous()

@@ -59,11 +59,36 @@ class VCLM_HF(nn.Module):
         logits_warper = self._get_logits_warper(top_k=top_k, top_p=top_p, typical_p=None, temperature=temperature, num_beams=1)
         nlls, num_tokens = torch.zeros(image_tokens.shape[0]).to(device), torch.zeros(image_tokens.shape[0]).to(device)
         is_reach_eos = torch.zeros(image_tokens.shape[0]).bool().to(device)
-        kv_cache = {}
-        self_cache = {"max_len": max_text_length} if (use_kv_cache and not teacher_forcing) else None
+        use_cache = use_kv_cache and not teacher_forcing
+        import os
+        use_graph = use_cache and image_tokens.is_cuda and os.environ.get("LAVILA_B200_DECODE_GRAPH", "1") == "1"
+        st = self._decode_state(image_tokens, max_text_length) if use_graph else None
+        kv_cache = st["ctx"] if st is not None else {}
+        self_cache = st["self"] if st is not None else ({"max_len": max_text_length} if use_cache else None)
         with torch.no_grad():
             for i in range(max_text_length - 1):
-                if self_cache is not None:
+                if st is not None and i >= 1:
+                    # positions >= 1: one decoder step with static arguments (position in device memory); run eagerly once,
+                    # then captured in a CUDA graph and replayed -- ~680 launches per step become one graph launch
+                    st["ids"].copy_(condition_text_ids[:, -1:])
+                    st["dyn"]["pos_idx"].fill_(i)
+                    st["dyn"]["lk_dev"].fill_(i + 1)
+                    if st["graph"] is not None:
+                        st["graph"].replay()
+                        out = st["out"]
+                    elif not st["warm"]:
+                        out = self.text_decoder(st["ids"], encoder_hidden_states=image_tokens, last_only=True,
+                                                ctx_kv_cache=kv_cache, self_kv_cache=self_cache, dyn=st["dyn"])
+                        st["warm"] = True
+                    else:
+                        g = torch.cuda.CUDAGraph()
+                        with torch.cuda.graph(g):
+                            st["out"] = self.text_decoder(st["ids"], encoder_hidden_states=image_tokens, last_only=True,
+                                                          ctx_kv_cache=kv_cache, self_kv_cache=self_cache, dyn=st["dyn"])
+                        st["graph"] = g
+                        g.replay()                      # capture records, replay executes
+                        out = st["out"]
+                elif self_cache is not None:
                     out = self.text_decoder(condition_text_ids[:, -1:], encoder_hidden_states=image_tokens, last_only=True,
                                             ctx_kv_cache=kv_cache, self_kv_cache=self_cache, past_len=i)
                 else:
@@ -90,6 +115,26 @@ class VCLM_HF(nn.Module):
                     condition_text_ids = torch.cat((generated_text_ids, next_token), dim=1)
                 generated_text_ids = torch.cat((generated_text_ids, next_token), dim=1)
         return generated_text_ids, torch.exp(nlls / num_tokens)
+
+    def _decode_state(self, image_tokens, max_len):
+        """Persistent buffers of the graph-captured decoding step, keyed by (sequences, max length, device, weight versions):
+        per-layer self-attention KV caches, cross-attention K/V buffers (refilled in place for every new batch of clips),
+        the static input ids / position scalars and the captured graph.  Weights changing (training) drop the state."""
+        ver = sum(p._version for p in self.text_decoder.parameters())
+        key = (image_tokens.shape[0], image_tokens.shape[1], max_len, str(image_tokens.device), ver)
+        store = self.__dict__.setdefault("_decode_states", {})
+        st = store.get(key)
+        if st is None:
+            store.clear()      # one live configuration at a time (the caches are large)
+            dev = image_tokens.device
+            st = {"ctx": {}, "self": {"max_len": max_len}, "graph": None, "warm": False, "out": None,
+                  "ids": torch.zeros(image_tokens.shape[0], 1, dtype=torch.int64, device=dev),
+                  "dyn": {"pos_idx": torch.zeros(1, dtype=torch.int64, device=dev),
+                          "lk_dev": torch.ones(1, dtype=torch.int32, device=dev)}}
+            store[key] = st
+        # the cross-attention K/V buffers hold the previous clips: every layer recomputes its own at step 0
+        st["ctx"]["_stale"] = {k for k in st["ctx"] if isinstance(k, int)}
+        return st
 
     def _get_logits_warper(self, top_k=None, top_p=None, typical_p=None, temperature=None, num_beams=None,
                            renormalize_logits=None):

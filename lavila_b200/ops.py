@@ -115,6 +115,14 @@ def flash_attn_fwd(q, k, v, out, B, H, Lq, Lk, *, q_rows, kv_rows, ld_q, ld_kv, 
     L.check(rc, "lv_flash_attn_fwd")
 
 
+def flash_attn_fwd_dyn(q, k, v, out, B, H, Lq, lk_dev, *, q_rows, kv_rows, ld_q, ld_kv, ld_out, kv_head_stride=64, causal=False,
+                       scale=0.125):
+    """lv_flash_attn_fwd with the key count in device memory (int32 tensor lk_dev) -- CUDA-graph friendly."""
+    rc = L.lib().lv_flash_attn_fwd_dyn(q.data_ptr(), ld_q, q_rows, k.data_ptr(), v.data_ptr(), ld_kv, kv_rows, kv_head_stride,
+                                       out.data_ptr(), ld_out, B, H, Lq, lk_dev.data_ptr(), int(causal), float(scale), _stream())
+    L.check(rc, "lv_flash_attn_fwd_dyn")
+
+
 def cls_attn_fwd(qkv, out, lse, B, H, N):
     rc = L.lib().lv_cls_attn_fwd(qkv.data_ptr(), qkv.stride(0), out.data_ptr(), out.stride(0), lse.data_ptr(), B, H, N,
                                  _stream())

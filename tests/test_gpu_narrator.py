@@ -101,6 +101,15 @@ def test_kv_cached_decoding_equals_full_prefix():
         outs.append(m.generate(tok, t, max_text_length=8, top_p=0.95, temperature=0.7, num_return_sequences=3, use_kv_cache=use))
     assert torch.equal(outs[0][0], outs[1][0])
     assert rel_l2(outs[1][1], outs[0][1]) < 1e-4
+    # the CUDA-graph state (KV buffers, captured step) is reused for the next batch of clips: same answers as a cold run
+    assert m._decode_states and next(iter(m._decode_states.values()))["graph"] is not None
+    tok2 = m.encode_image(frames.flip(0).contiguous())
+    outs2 = []
+    for use in (True, False):
+        torch.manual_seed(6)
+        outs2.append(m.generate(tok2, t, max_text_length=8, top_p=0.95, temperature=0.7, num_return_sequences=3, use_kv_cache=use))
+    assert torch.equal(outs2[0][0], outs2[1][0])
+    assert rel_l2(outs2[0][1], outs2[1][1]) < 1e-4
 
 
 @pytest.mark.parametrize("B,H,Lq,Lk,mqa,causal", [(2, 3, 5, 40, False, False), (2, 25, 77, 256, False, False),

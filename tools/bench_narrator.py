@@ -23,10 +23,13 @@ def main():
     ap.add_argument("--max-len", type=int, default=77)
     ap.add_argument("--impl", default="ours", choices=["ours", "eager"])
     ap.add_argument("--decoder", default="xl", choices=["xl", "base"])
+    ap.add_argument("--no-graph", action="store_true", help="ours: KV-cached decoding without the CUDA-graph replay of the step")
     ap.add_argument("--no-kv-cache", action="store_true", help="ours: re-run the whole prefix every step (reference algorithm)")
     ap.add_argument("--encoder", default="base", choices=["base", "large"],
                     help="large = TSF-L/14 224px: VCLM_OPENAI_TIMESFORMER_LARGE_GPT2_XL, the model BASELINE config 4 names")
     a = ap.parse_args()
+    if a.no_graph:
+        os.environ["LAVILA_B200_DECODE_GRAPH"] = "0"
     dev = torch.device("cuda", 0)
     torch.manual_seed(0)
     tok = SimpleNamespace(bos_token_id=50256, eos_token_id=50256, pad_token_id=0)
@@ -76,7 +79,7 @@ def main():
         ids, _ = run()
         torch.cuda.synchronize()
         dt = time.time() - t0
-        print(json.dumps({"impl": a.impl, "encoder": a.encoder, "decoder": a.decoder, "kv_cache": (a.impl == "ours" and not a.no_kv_cache),
+        print(json.dumps({"impl": a.impl, "encoder": a.encoder, "decoder": a.decoder, "kv_cache": (a.impl == "ours" and not a.no_kv_cache), "cuda_graph": (a.impl == "ours" and not a.no_kv_cache and not a.no_graph),
                           "batch": a.batch, "returns": R, "frames": a.frames,
                           "tokens": int(ids.shape[1]), "seconds": round(dt, 3), "clips_per_s": round(a.batch / dt, 3),
                           "sequences_per_s": round(a.batch * R / dt, 3),
