@@ -79,6 +79,15 @@ int lv_gemm_bf16(const void* A, int64_t lda, int a_mn, const void* B, int64_t ld
 int lv_gemm_bf16_2cta(const void* A, int64_t lda, int a_mn, const void* B, int64_t ldb, int b_mn, int64_t M, int64_t N,
                       int64_t K, int k_splits, const LvGemmEpilogue* epi, void* stream);
 
+/* Skinny GEMM for KV-cached decoding (M = sequences being decoded, up to a few hundred rows): C = epilogue(A[M,K] x W) with
+ * W stored [K][ldb], N contiguous (HF Conv1D, gpt2_gated.py:47; the b_mn = 1 layout above).  Weight streaming is the
+ * roofline: the grid is (N/64) x splits x ceil(M/64) CTAs so that every SM streams W; partial tiles go to `workspace`
+ * (fp32 [splits][M][N], caller-allocated) with plain stores and are summed in order by a second kernel that applies the
+ * epilogue (deterministic: no atomics).  Supported flags: BIAS, GELU_TANH, SQRELU, SCALE[_TANH], RESID, OUT_F32.
+ * N % 64 == 0, K % 64 == 0.  lv_gemm_skinny_splits returns the split count to use (0 = shape not supported). */
+int lv_gemm_skinny_splits(int64_t M, int64_t N, int64_t K);
+int lv_gemm_skinny_bf16(const void* A, int64_t lda, const void* W, int64_t ldb, int64_t M, int64_t N, int64_t K,
+                        float* workspace, int splits, const LvGemmEpilogue* epi, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * LayerNorm over the last dimension (one warp per row, fp32 statistics).  D % 128 == 0, D <= 1024.

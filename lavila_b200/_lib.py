@@ -45,6 +45,11 @@ def _declare(lib):
                                  ctypes.POINTER(LvGemmEpilogue), c_void_p]
     lib.lv_gemm_bf16_2cta.restype = c_int
     lib.lv_gemm_bf16_2cta.argtypes = lib.lv_gemm_bf16.argtypes
+    lib.lv_gemm_skinny_splits.restype = c_int
+    lib.lv_gemm_skinny_splits.argtypes = [c_int64, c_int64, c_int64]
+    lib.lv_gemm_skinny_bf16.restype = c_int
+    lib.lv_gemm_skinny_bf16.argtypes = [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p, c_int,
+                                        ctypes.POINTER(LvGemmEpilogue), c_void_p]
     from . import _decl  # remaining entry points
     _decl.declare(lib)
 

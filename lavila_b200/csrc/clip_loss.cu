@@ -425,7 +425,7 @@ clip_loss_fwd_gather_kernel(const float* __restrict__ img_local, const float* __
       long long spins = 0;
       while (ld_acquire_sys(flag) != step) {
         __nanosleep(200);
-        if (++spins > (1ll << 24)) { timed_out = 1; break; }   // ~3+ s: a peer is gone; fail loudly instead of hanging
+        if (++spins > (1ll << 27)) { timed_out = 1; break; }   // ~30 s: a peer is gone; fail loudly (NaN) instead of hanging
       }
     }
     __syncthreads();

@@ -51,7 +51,10 @@ class Conv1D(nn.Module):
 def _linear(x_bf16, conv, M, out, flags=0, **kw):
     """out[M, nf] = epilogue(x @ W + b) with W stored [in, out] (B operand MN-major)."""
     K, N = conv.weight.shape
-    return ops.gemm(x_bf16, SHADOW.get(conv.weight), M, N, K, out, b_mn=1, flags=flags | L.EPI_BIAS, bias=conv.bias, **kw)
+    w = SHADOW.get(conv.weight)
+    if M <= ops.SKINNY_MAX_M and ops.gemm_skinny(x_bf16, w, M, N, K, out, flags=flags | L.EPI_BIAS, bias=conv.bias, **kw):
+        return out     # decoding-sized M: weight-streaming kernel (csrc/gemm_skinny.cu)
+    return ops.gemm(x_bf16, w, M, N, K, out, b_mn=1, flags=flags | L.EPI_BIAS, bias=conv.bias, **kw)
 
 
 class GPT2Attention(nn.Module):

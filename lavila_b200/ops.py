@@ -50,6 +50,36 @@ def gemm(A, B, M, N, K, out, *, a_mn=0, b_mn=0, flags=0, out2=None, bias=None, r
     return out
 
 
+SKINNY_MAX_M = 512      # decode-sized GEMMs (rows = sequences) stream W from every SM instead of N/256 CTAs
+
+
+def gemm_skinny(A, W, M, N, K, out, *, flags=0, bias=None, resid=None, scale=None):
+    """out[M,N] = epilogue(A[M,K] @ W[K,N]) for small M (lv_gemm_skinny_bf16); returns False if the shape is not supported
+    (the caller then uses the tiled GEMM).  W is the [K, N] matrix itself (HF Conv1D weight), bf16."""
+    if M > SKINNY_MAX_M:
+        return False
+    splits = L.lib().lv_gemm_skinny_splits(M, N, K)
+    if splits <= 0:
+        return False
+    _check_cuda(A, W, out)
+    e = L.LvGemmEpilogue()
+    if out.dtype == F32:
+        flags |= L.EPI_OUT_F32
+    e.flags = flags
+    e.out, e.ldo = out.data_ptr(), out.stride(0)
+    if bias is not None:
+        e.bias = bias.data_ptr()
+    if resid is not None:
+        e.resid, e.ldr = resid.data_ptr(), resid.stride(0)
+    if scale is not None:
+        e.scale_ptr = scale.data_ptr()
+    ws = torch.empty(splits * M * N, device=A.device, dtype=F32)
+    rc = L.lib().lv_gemm_skinny_bf16(A.data_ptr(), A.stride(0), W.data_ptr(), W.stride(0), M, N, K, ws.data_ptr(), splits,
+                                     ctypes.byref(e), _stream())
+    L.check(rc, "lv_gemm_skinny_bf16")
+    return True
+
+
 USE_2CTA_GEMM = True    # 256x256 CTA-pair tiles (lv_gemm_bf16_2cta) whenever M >= 256
 
 

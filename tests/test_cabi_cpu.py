@@ -31,7 +31,8 @@ def test_decl_table_matches_header():
     from lavila_b200 import _decl
     declared = set(_declared())
     assert set(_decl.SIGNATURES) <= declared, set(_decl.SIGNATURES) - declared
-    known = set(_decl.SIGNATURES) | {"lv_version", "lv_last_error", "lv_launch_count", "lv_gemm_bf16", "lv_gemm_bf16_2cta"}
+    known = set(_decl.SIGNATURES) | {"lv_version", "lv_last_error", "lv_launch_count", "lv_gemm_bf16", "lv_gemm_bf16_2cta",
+                                         "lv_gemm_skinny_bf16", "lv_gemm_skinny_splits"}   # declared in _lib.py (struct args)
     assert declared <= known, declared - known
 
 

@@ -133,3 +133,37 @@ def test_flash_attention(B, H, Lq, Lk, mqa, causal):
         s = s.masked_fill(~mask, float("-inf"))
     ref = (torch.softmax(s, dim=-1) @ vf).permute(0, 2, 1, 3)
     assert rel_l2(out, ref) < 1e-2
+
+
+@pytest.mark.parametrize("M,N,K,flags", [(32, 1600, 1600, "bias"), (5, 4800, 1600, "bias"), (320, 6400, 1600, "gelu"),
+                                         (32, 1600, 6400, "resid_gate"), (70, 768, 768, "sqrelu"), (32, 1600, 1600, "resid")])
+def test_skinny_gemm(M, N, K, flags):
+    """lv_gemm_skinny_bf16 (decode-sized GEMMs, csrc/gemm_skinny.cu) against fp32 torch on the same bf16 operands, every epilogue
+    the gated GPT-2 uses; two runs are bit-identical (deterministic split-K)."""
+    from lavila_b200 import ops, _lib as L
+    torch.manual_seed(7)
+    A = (torch.randn(M, K, device=DEV) * 0.5).to(torch.bfloat16)
+    W = (torch.randn(K, N, device=DEV) * 0.05).to(torch.bfloat16)
+    bias = torch.randn(N, device=DEV)
+    resid = torch.randn(M, N, device=DEV)
+    gate = torch.tensor(0.7, device=DEV)
+    acc = A.float() @ W.float() + bias
+    if flags == "bias":
+        fl, kw, ref, dt = 0, {}, acc, torch.bfloat16
+    elif flags == "gelu":
+        fl, kw, dt = L.EPI_GELU_TANH, {}, torch.bfloat16
+        ref = torch.nn.functional.gelu(acc, approximate="tanh")
+    elif flags == "sqrelu":
+        fl, kw, ref, dt = L.EPI_SQRELU, {}, torch.relu(acc) ** 2, torch.bfloat16
+    elif flags == "resid":
+        fl, kw, ref, dt = L.EPI_RESID, dict(resid=resid), acc + resid, torch.float32
+    else:
+        fl, kw, dt = L.EPI_RESID | L.EPI_SCALE | L.EPI_SCALE_TANH, dict(resid=resid, scale=gate), torch.float32
+        ref = torch.tanh(gate) * acc + resid
+    outs = []
+    for _ in range(2):
+        out = torch.empty(M, N, device=DEV, dtype=dt)
+        assert ops.gemm_skinny(A, W, M, N, K, out, flags=fl | L.EPI_BIAS, bias=bias, **kw)
+        outs.append(out)
+    assert torch.equal(outs[0], outs[1])
+    assert_close_bf16(outs[0], ref, "skinny gemm %s" % flags, rel=1e-2)
