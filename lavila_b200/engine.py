@@ -9,6 +9,9 @@ Two reusable sub-blocks cover both towers:
     attn_sub : y = resid + gate * Proj(Attention(QKV(LN(x_ln))))      (time / space / causal)
     mlp_sub  : y = r + FC2(QuickGELU(FC1(LN(r))))
 """
+import contextlib
+import os
+
 import torch
 
 from . import _lib as L
@@ -66,9 +69,6 @@ def take_bf16(t_f32):
 # node returns).  With WGRAD_STREAM on they are enqueued on a second CUDA stream, so the tensor-core-bound split-K wgrad
 # GEMMs overlap the chain's HBM-bound kernels (LayerNorm backward, CLS / time attention) and the HBM-bound bias column
 # sums overlap the chain's GEMMs.  Every autograd node joins the side stream before it returns its gradients.
-import contextlib
-import os
-
 WGRAD_STREAM = os.environ.get("LAVILA_B200_WGRAD_STREAM", "0") == "1"
 _SIDE = {}
 
