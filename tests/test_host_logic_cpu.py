@@ -1,0 +1,79 @@
+"""Host-side logic that needs no GPU: the FLOP model bench.py reports against, GEMM split heuristics,
+loss-module contracts, model factories' parameter naming (weight-decay grouping of main_pretrain.py:199-213)."""
+import math
+
+import pytest
+import torch
+
+
+def test_flop_model_matches_survey():
+    import bench
+    assert abs(bench.flops_per_clip_train() / 1e12 - 2.2354) < 1e-3                     # cfg 2/3: 2.236 TF / clip
+    f5 = bench.flops_per_clip_train(T=32, **bench.MODELS["large336"][2])
+    assert abs(f5 / 1e12 - 47.97) < 0.02                                                # cfg 5: 47.97 TF / clip
+    # per-block forward figure of SURVEY 8(a) a4: 61.29 GF (N = 3137, D = 768)
+    N, D, T, n = 3137, 768, 16, 196
+    f_blk = 32 * N * D * D + 4 * D * ((T * n) * (T + n + 2) + 2 * N)
+    assert abs(f_blk / 1e9 - 61.29) < 0.01
+
+
+def test_wgrad_split_heuristic_bounds():
+    from lavila_b200 import ops
+    for m_out, n_in, tokens in ((768, 768, 200768), (2304, 768, 200768), (3072, 768, 200768), (768, 3072, 200768),
+                                (512, 512, 4928), (256, 768, 64)):
+        s = ops.wgrad_splits(m_out, n_in, tokens)
+        assert 1 <= s <= (tokens + 63) // 64
+
+
+def test_sslcliploss_module_contract():
+    from lavila_b200.models.loss import SSLCLIPLoss, CLIPLoss
+    m = SSLCLIPLoss(scale_init=0.08)
+    assert list(m.state_dict().keys()) == ["logit_scale_pseudo"]                        # loss.py:140 (checkpointed, main_pretrain.py:398)
+    assert abs(float(m.logit_scale_pseudo.detach()) - math.log(1 / 0.08)) < 1e-6
+    assert m.logit_scale_pseudo.requires_grad
+    assert not SSLCLIPLoss(freeze_scale=True).logit_scale_pseudo.requires_grad
+    with pytest.raises(NotImplementedError):                                            # loss.py:167-168
+        SSLCLIPLoss(world_size=2, use_vissl=False)({"image_embed": None, "text_embed": None, "logit_scale": None}, None)
+    assert list(CLIPLoss().state_dict().keys()) == []
+
+
+def test_get_loss_and_metric_names():
+    from types import SimpleNamespace
+    from lavila_b200.models import models as M
+    args = SimpleNamespace(contrastive_use_vissl=True, rank=3, world_size=8)
+    crit = M.get_loss("CLIP_OPENAI_TIMESFORMER_BASE", args)
+    assert crit.use_vissl and crit.rank == 3 and crit.world_size == 8 and crit.cache_labels
+    assert M.get_metric_names("CLIP_OPENAI_TIMESFORMER_BASE") == ["loss", "clip_loss", "clip_acc"]
+    assert M.loss.SSLCLIPLoss is not None                                               # main_pretrain.py:189 reaches it this way
+
+
+def test_weight_decay_grouping_names():
+    """main_pretrain.py:199-213 puts a parameter in the no-decay group iff ndim < 2 or its name contains 'bias', 'ln' or 'bn':
+    the mirror must expose the reference's names so the same parameters land in the same group."""
+    import contextlib
+    import io
+    import bench
+    from lavila_b200.models import models as M
+    with contextlib.redirect_stdout(io.StringIO()):
+        model = M.CLIP_OPENAI_TIMESFORMER_BASE(num_frames=4, project_embed_dim=256)
+    groups = bench.param_groups(model)
+    decay = {id(p) for p in groups[0]["params"]}
+    named = dict(model.named_parameters())
+    assert id(named["visual.blocks.0.attn.qkv.weight"]) in decay
+    assert id(named["transformer.resblocks.0.mlp.c_fc.weight"]) in decay
+    assert id(named["visual.pos_embed"]) in decay and id(named["visual.temporal_embed"]) in decay   # 3-D, no 'ln' in the name
+    for n in ("visual.blocks.0.attn.qkv.bias", "visual.ln_pre.weight", "ln_final.weight", "logit_scale",
+              "transformer.resblocks.0.ln_1.weight"):
+        assert id(named[n]) not in decay, n
+    assert id(named["visual.blocks.0.norm1.weight"]) not in decay                       # ndim 1
+    assert abs(sum(p.numel() for p in model.parameters()) / 1e6 - 177.7) < 0.5
+
+
+def test_narrator_factories_exist_with_reference_names():
+    from lavila_b200.models import models as M
+    for name in ("VCLM_OPENAI_TIMESFORMER_BASE_GPT2", "VCLM_OPENAI_TIMESFORMER_BASE_GPT2_XL", "VCLM_OPENAI_TIMESFORMER_LARGE_GPT2",
+                 "VCLM_OPENAI_TIMESFORMER_LARGE_GPT2_XL", "VCLM_OPENAI_TIMESFORMER_LARGE_336PX_GPT2_XL",
+                 "CLIP_OPENAI_TIMESFORMER_BASE", "CLIP_OPENAI_TIMESFORMER_LARGE", "CLIP_OPENAI_TIMESFORMER_LARGE_336PX",
+                 "CLIP_OPENAI_TIMESFORMER_BASE_DISTILBERT_BASE", "CLIP_OPENAI_TIMESFORMER_LARGE_DISTILBERT_BASE",
+                 "CLIP_OPENAI_TIMESFORMER_LARGE_336PX_DISTILBERT_BASE"):
+        assert callable(getattr(M, name)), name
