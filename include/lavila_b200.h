@@ -30,6 +30,13 @@ int lv_version(void);
 const char* lv_last_error(void);
 /* Number of kernels this library has launched in this process (all threads). bench.py reports it. */
 int64_t lv_launch_count(void);
+/* Bytes of caller-allocated scratch an op needs (the library allocates nothing); -1 = unknown op / bad shape.
+ *   LV_WS_GEMM_SKINNY (M, N, K)    workspace of lv_gemm_skinny_bf16
+ *   LV_WS_ATTN_BWD_DCLS (B, H, 0)  dcls_kv of the attention backward entry points (must be zeroed)
+ *   LV_WS_CLIP_LOSS (Ng, 0, 0)     lse_img + lse_txt + partial + control words + result of the loss entry points
+ *   LV_WS_P2P_BLOCK (Bl, E, 0)     one rank's symmetric block for lv_clip_loss_fwd_gather */
+enum { LV_WS_GEMM_SKINNY = 1, LV_WS_ATTN_BWD_DCLS = 2, LV_WS_CLIP_LOSS = 3, LV_WS_P2P_BLOCK = 4 };
+int64_t lv_workspace_bytes(int op, int64_t a, int64_t b, int64_t c);
 
 /* ------------------------------------------------------------------------------------------------
  * GEMM (tcgen05 tensor cores, TMA-staged operands, TMEM accumulators)

@@ -40,6 +40,8 @@ def _declare(lib):
     lib.lv_version.restype = c_int
     lib.lv_last_error.restype = ctypes.c_char_p
     lib.lv_launch_count.restype = c_int64
+    lib.lv_workspace_bytes.restype = c_int64
+    lib.lv_workspace_bytes.argtypes = [c_int, c_int64, c_int64, c_int64]
     lib.lv_gemm_bf16.restype = c_int
     lib.lv_gemm_bf16.argtypes = [c_void_p, c_int64, c_int, c_void_p, c_int64, c_int, c_int64, c_int64, c_int64, c_int,
                                  ctypes.POINTER(LvGemmEpilogue), c_void_p]

@@ -81,6 +81,26 @@ int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t inner, uint64
 
 }  // namespace lv
 
+extern "C" int lv_gemm_skinny_splits(int64_t M, int64_t N, int64_t K);
+
+extern "C" int64_t lv_workspace_bytes(int op, int64_t a, int64_t b, int64_t c) {
+  if (a <= 0 || b < 0 || c < 0) return -1;
+  switch (op) {
+    case LV_WS_GEMM_SKINNY: {                       // (M, N, K) -> fp32 [splits][M][N]
+      const int s = lv_gemm_skinny_splits(a, b, c);
+      return s > 0 ? (int64_t)s * a * b * 4 : -1;
+    }
+    case LV_WS_ATTN_BWD_DCLS:                       // (B, H) -> fp32 [B][H][2][64], zeroed by the caller
+      return b > 0 ? a * b * 2 * 64 * 4 : -1;
+    case LV_WS_CLIP_LOSS:                           // (Ng) -> lse_img[Ng] + lse_txt[Ng] + partial[2 Ng] fp32 (+ 4 control words, result[6])
+      return a * 4 * 4 + 4 * 4 + 6 * 4;
+    case LV_WS_P2P_BLOCK:                           // (Bl, E) -> one rank's symmetric block: 2 slots x (Bl x 2E fp32 + 32 words)
+      return b > 0 ? 2 * (a * 2 * b + 32) * 4 : -1;
+    default:
+      return -1;
+  }
+}
+
 extern "C" {
 int lv_version(void) { return LV_ABI_VERSION; }
 const char* lv_last_error(void) { return lv::g_err; }
