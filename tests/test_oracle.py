@@ -128,3 +128,40 @@ def test_ssl_clip_loss_multirank_semantics():
         torch.testing.assert_close(W * gtx[k * B:(k + 1) * B], r[k]["grad_text"], rtol=1e-4, atol=1e-7)
         torch.testing.assert_close(gs, r[k]["grad_scale"], rtol=1e-4, atol=1e-7)
         torch.testing.assert_close(gp, r[k]["grad_scale_pseudo"], rtol=1e-4, atol=1e-7)
+
+
+# ----------------------------------------------------------------------------------------------- extra reference goldens
+EXTRA = torch.load(os.path.join(os.path.dirname(__file__), "golden", "dual_encoder_extra.pt"), weights_only=False)
+
+
+@pytest.mark.parametrize("case", ["p14", "wide_text", "fewframes"])
+def test_oracle_matches_reference_extra_geometries(case):
+    """Patch 14 / 4 heads / depth 3 / gated; a deeper, wider text tower; an 8-frame model fed 4-frame clips
+    (tests/golden/make_golden_extra.py): outputs, loss, accuracy and every parameter gradient of the unmodified reference."""
+    c = EXTRA[case]
+    cfg = c["cfg"]
+    p = O.init_params(cfg, seed=c["param_seed"], gated=c["gated"])
+    for k, v in c["param_checksum"].items():
+        assert abs(float(p[k].double().sum()) - v) <= 1e-6 * max(1.0, abs(v)), k
+    frames, text = O.synthetic_batch(cfg, c["batch"], seed=c["input_seed"], frames=c.get("frames"))
+    assert abs(float(frames.double().sum()) - c["frames_checksum"]) < 1e-6 * frames.numel()
+    assert torch.equal(text, c["text"])
+    p = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+    out = O.clip_forward(frames, text, p, cfg, norm_embed=c["norm_embed"])
+    torch.testing.assert_close(out["image_embed"], c["image_embed"], **TOL)
+    torch.testing.assert_close(out["text_embed"], c["text_embed"], **TOL)
+    ld = O.clip_loss(out["image_embed"], out["text_embed"], out["logit_scale"])
+    torch.testing.assert_close(ld["loss"], c["loss"], rtol=1e-4, atol=1e-4)
+    assert float(ld["clip_acc"]) == float(c["clip_acc"])
+    ld["loss"].backward()
+    for name, ref in c["grads"].items():
+        g = p[name].grad
+        assert g is not None, name
+        # fp32 summation-order noise scales with the largest entry (a few entries are near-cancelling sums): atol relative to it
+        if "full" in ref:
+            want = ref["full"].reshape(g.shape)
+            torch.testing.assert_close(g, want, rtol=2e-3, atol=2e-3 * float(want.abs().max()) + 1e-9, msg=lambda m: name + ": " + m)
+        else:
+            want = ref["sample"]
+            torch.testing.assert_close(g.flatten()[ref["idx"]], want, rtol=2e-3, atol=2e-3 * float(want.abs().max()) + 1e-9,
+                                       msg=lambda m: name + ": " + m)
