@@ -44,3 +44,27 @@ def test_warper_matches_transformers():
     got = ON.warp_logits(logits, temperature=0.7, top_p=0.95)
     assert torch.equal(torch.isinf(got), torch.isinf(ref))          # the kept set is an index operation: exact
     torch.testing.assert_close(got[~torch.isinf(got)], ref[~torch.isinf(ref)])
+
+
+EXTRA = torch.load(os.path.join(os.path.dirname(__file__), "golden", "narrator_extra.pt"), weights_only=False)
+
+
+def _extra_case(name):
+    c = EXTRA[name]
+    cfg = c["cfg"]
+    p = ON.init_narrator_params(cfg, seed=c["param_seed"])
+    for k, v in c["param_checksum"].items():
+        assert abs(float(p[k].double().sum()) - v) <= 1e-6 * max(1.0, abs(v)), k
+    frames, _ = synthetic_batch(dict(cfg["visual"], context_length=8, vocab_size=8), 2, seed=c["frames_seed"])
+    return c, cfg, p, frames
+
+
+def test_narrator_oracle_extra_geometries():
+    """Patch-14 encoder + cross-attention every 3rd decoder layer, and cross-attention in every layer
+    (tests/golden/make_golden_narrator_extra.py)."""
+    for name in ("p14_freq3", "freq1"):
+        c, cfg, p, frames = _extra_case(name)
+        torch.testing.assert_close(ON.vclm_encode_image(frames, p, cfg), c["image_tokens"], **TOL)
+        out = ON.vclm_forward(frames, c["text"], p, cfg)
+        torch.testing.assert_close(out["text_tokens_logits"], c["logits"], rtol=1e-3, atol=1e-4)
+        assert torch.equal(out["labels"], c["labels"])
