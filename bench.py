@@ -156,8 +156,7 @@ def run_ours(args):
     if world > 1:
         import datetime
         dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=240))
-    import lavila_b200
-    from lavila_b200 import _lib, engine, ops
+    from lavila_b200 import _lib, ops
     from lavila_b200.models import models as M
     from lavila_b200.models.loss import CLIPLoss
 

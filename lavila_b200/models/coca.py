@@ -4,7 +4,6 @@ shared 64-d key/value head (multi-query).  `parallel_ff` is never enabled by the
 import torch
 import torch.nn as nn
 
-from .. import _lib as L
 from .. import ops
 from ..engine import SHADOW
 
