@@ -165,3 +165,32 @@ def test_oracle_matches_reference_extra_geometries(case):
             want = ref["sample"]
             torch.testing.assert_close(g.flatten()[ref["idx"]], want, rtol=2e-3, atol=2e-3 * float(want.abs().max()) + 1e-9,
                                        msg=lambda m: name + ": " + m)
+
+
+def test_oracle_block_at_tsfb_geometry_matches_reference():
+    """One SpaceTimeBlock at the REAL TSF-B geometry (D = 768, 12 heads, 16 x 196 patches, tanh-gated), forward and every
+    gradient, against the unmodified reference (tests/golden/make_golden_block.py; 4096-entry samples + norms).  The GPU test
+    tests/test_gpu_model.py::test_block_midsize_vs_oracle compares the kernels with this same oracle at this same geometry."""
+    from tests.golden.make_golden_block import block_inputs, block_params
+    g = torch.load(os.path.join(os.path.dirname(__file__), "golden", "block_tsfb.pt"), weights_only=False)
+    geo = g["geometry"]
+    params = block_params(g["param_seed"])
+    for k, v in g["param_checksum"].items():
+        assert abs(float(params[k].double().sum()) - v) <= 1e-6 * max(1.0, abs(v)), k
+    x, dy = block_inputs(g["input_seed"])
+    assert abs(float(x.double().sum()) - g["x_checksum"]) < 1e-6 * x.numel()
+    p = {"b." + k: v.clone().requires_grad_(True) for k, v in params.items()}
+    x.requires_grad_(True)
+    y = O.space_time_block(x, p, "b.", geo["H"], geo["T"], geo["n"])
+    y.backward(dy)
+
+    def check(t, ref, name, rtol):
+        got = t.detach().float().flatten()[ref["idx"]]
+        scale = float(ref["sample"].abs().max())
+        torch.testing.assert_close(got, ref["sample"], rtol=rtol, atol=rtol * scale, msg=lambda m: name + ": " + m)
+        torch.testing.assert_close(t.detach().float().norm(), ref["norm"], rtol=1e-4, atol=0, msg=lambda m: name + " norm: " + m)
+
+    check(y, g["y"], "y", 1e-4)
+    check(x.grad, g["dx"], "dx", 1e-3)
+    for k, ref in g["grads"].items():
+        check(p["b." + k].grad, ref, "d" + k, 2e-3)
