@@ -249,6 +249,40 @@ def cls_query_attn_bwd(q, kv, out, dout, lse, dq, dkv, B, H, N):
     dkv.copy_(torch.cat((gk.reshape(B * N, D), gv.reshape(B * N, D)), 1).to(dkv.dtype))
 
 
+def flash_attn_fwd(q, k, v, out, B, H, Lq, Lk, *, q_rows, kv_rows, ld_q, ld_kv, ld_out, kv_head_stride=64, causal=False,
+                   scale=0.125):
+    """Q element (b,h,i,d) at q[(b*q_rows+i)*ld_q + h*64 + d]; K/V (b,h,j,d) at k[(b*kv_rows+j)*ld_kv + h*kv_head_stride + d];
+    causal: key j visible to query i iff j <= i + (Lk - Lq)."""
+    qq = _mat(q, B * q_rows, H * 64, ld_q).float().view(B, q_rows, H, 64)[:, :Lq]
+    width = 64 + (H - 1) * kv_head_stride
+    kk = _mat(k, B * kv_rows, width, ld_kv).float().view(B, kv_rows, width)[:, :Lk]
+    vv = _mat(v, B * kv_rows, width, ld_kv).float().view(B, kv_rows, width)[:, :Lk]
+    heads = [slice(h * kv_head_stride, h * kv_head_stride + 64) for h in range(H)]
+    kh = torch.stack([kk[..., sl] for sl in heads], 2)                    # [B, Lk, H, 64]
+    vh = torch.stack([vv[..., sl] for sl in heads], 2)
+    s = torch.einsum("bihd,bjhd->bhij", qq, kh) * scale
+    if causal:
+        i = torch.arange(Lq).view(Lq, 1)
+        j = torch.arange(Lk).view(1, Lk)
+        s = s.masked_fill(j > i + (Lk - Lq), float("-inf"))
+    o = torch.einsum("bhij,bjhd->bihd", torch.softmax(s, -1), vh)
+    _mat(out, B * q_rows, H * 64, ld_out).view(B, q_rows, H * 64)[:, :Lq] = o.reshape(B, Lq, H * 64).to(out.dtype)
+
+
+def flash_attn_fwd_dyn(q, k, v, out, B, H, Lq, lk_dev, **kw):
+    flash_attn_fwd(q, k, v, out, B, H, Lq, int(lk_dev.item()), **kw)
+
+
+SKINNY_MAX_M = 512
+
+
+def gemm_skinny(A, W, M, N, K, out, *, flags=0, bias=None, resid=None, scale=None):
+    if M > SKINNY_MAX_M or N % 64 or K % 64:
+        return False
+    gemm(A, W, M, N, K, out, b_mn=1, flags=flags, bias=bias, resid=resid, scale=scale)
+    return True
+
+
 # ------------------------------------------------------------------------------------------------------------------ glue
 def add_rows(dst, stride, src, R, W):
     d = _mat(dst, R, W, stride)
@@ -350,7 +384,7 @@ def clip_loss_bwd(img, txt, scale, lse_i, lse_t, gout, grad_scale, scale_grad_sc
 DOUBLES = ("gemm", "wgrad_splits", "layernorm_fwd", "layernorm_bwd", "group_attn_fwd", "group_attn_bwd", "cls_attn_fwd",
            "cls_attn_bwd", "cls_kv_finalize", "cls_query_attn_fwd", "cls_query_attn_bwd", "add_rows", "cast_bf16", "colsum_bf16",
            "patch_im2col", "embed_assemble", "embed_assemble_bwd", "text_embed", "text_embed_bwd", "argmax_i64", "gather_rows",
-           "l2norm_fwd", "l2norm_bwd", "clip_loss_fwd", "clip_loss_bwd")
+           "l2norm_fwd", "l2norm_bwd", "clip_loss_fwd", "clip_loss_bwd", "flash_attn_fwd", "flash_attn_fwd_dyn", "gemm_skinny")
 
 
 def install(monkeypatch):
