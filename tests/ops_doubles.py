@@ -381,10 +381,48 @@ def clip_loss_bwd(img, txt, scale, lse_i, lse_t, gout, grad_scale, scale_grad_sc
         d_scale += gout * scale_grad_scale * gs
 
 
+def _ssl_logits(img, txt, s, sp, gt):
+    m = gt[:, None] + gt[None, :]
+    c = torch.where(m == 2, s, torch.where(m == 1, torch.sqrt(sp * s), sp))
+    return c * (img @ txt.t())
+
+
+def ssl_clip_loss_fwd(img, txt, scale, scale_p, gt, Ng, E, lse_i, lse_t, partial, counter, result):
+    logits = _ssl_logits(img, txt, scale, scale_p, gt)
+    lab = torch.arange(Ng)
+    lse_i.copy_(torch.logsumexp(logits, 1))
+    lse_t.copy_(torch.logsumexp(logits.t(), 1))
+    ok = (logits.argmax(-1) == lab).float()
+    g = (gt == 1).float()
+    result[0] = (torch.nn.functional.cross_entropy(logits, lab) + torch.nn.functional.cross_entropy(logits.t(), lab)) / 2
+    result[1] = 100 * ok.mean()
+    result[2] = 100 * (ok * g).sum() / g.sum()
+    result[3] = 100 * (ok * (1 - g)).sum() / (1 - g).sum()
+    result[4], result[5] = g.sum(), (1 - g).sum()
+
+
+def ssl_clip_loss_bwd(img, txt, scale, scale_p, gt, lse_i, lse_t, gout, grad_scale, scale_grad_scale, Ng, E, r0, Nl, d_img, d_txt,
+                      d_scales):
+    with torch.enable_grad():
+        i, t = img.clone().requires_grad_(True), txt.clone().requires_grad_(True)
+        s, sp = scale.clone().requires_grad_(True), scale_p.clone().requires_grad_(True)
+        logits = _ssl_logits(i, t, s, sp, gt)
+        lab = torch.arange(Ng)
+        loss = (torch.nn.functional.cross_entropy(logits, lab) + torch.nn.functional.cross_entropy(logits.t(), lab)) / 2
+        gi, gtx, gs, gp = torch.autograd.grad(loss, (i, t, s, sp), allow_unused=True)
+    d_img.copy_(gout * grad_scale * gi[r0:r0 + Nl])
+    d_txt.copy_(gout * grad_scale * gtx[r0:r0 + Nl])
+    if gs is not None:
+        d_scales[0] += (gout * scale_grad_scale * gs).reshape(())
+    if gp is not None:
+        d_scales[1] += (gout * scale_grad_scale * gp).reshape(())
+
+
 DOUBLES = ("gemm", "wgrad_splits", "layernorm_fwd", "layernorm_bwd", "group_attn_fwd", "group_attn_bwd", "cls_attn_fwd",
            "cls_attn_bwd", "cls_kv_finalize", "cls_query_attn_fwd", "cls_query_attn_bwd", "add_rows", "cast_bf16", "colsum_bf16",
            "patch_im2col", "embed_assemble", "embed_assemble_bwd", "text_embed", "text_embed_bwd", "argmax_i64", "gather_rows",
-           "l2norm_fwd", "l2norm_bwd", "clip_loss_fwd", "clip_loss_bwd", "flash_attn_fwd", "flash_attn_fwd_dyn", "gemm_skinny")
+           "l2norm_fwd", "l2norm_bwd", "clip_loss_fwd", "clip_loss_bwd", "flash_attn_fwd", "flash_attn_fwd_dyn", "gemm_skinny",
+           "ssl_clip_loss_fwd", "ssl_clip_loss_bwd")
 
 
 def install(monkeypatch):

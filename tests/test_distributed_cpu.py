@@ -109,47 +109,14 @@ def test_cliploss_two_rank_host_logic_matches_reference():
     assert all(ret[r] for r in range(world)), dict(ret)
 
 
-def _ssl_logits(img, txt, s, sp, gt):
-    m = gt[:, None] + gt[None, :]
-    c = torch.where(m == 2, s, torch.where(m == 1, torch.sqrt(sp * s), sp))
-    return c * (img @ txt.t())
-
-
-def _double_ssl_fwd(img, txt, scale, scale_p, gt, Ng, E, lse_i, lse_t, partial, counter, result):
-    logits = _ssl_logits(img, txt, scale, scale_p, gt)
-    lab = torch.arange(Ng)
-    lse_i.copy_(torch.logsumexp(logits, 1))
-    lse_t.copy_(torch.logsumexp(logits.t(), 1))
-    ok = (logits.argmax(-1) == lab).float()
-    g = (gt == 1).float()
-    result[0] = (torch.nn.functional.cross_entropy(logits, lab) + torch.nn.functional.cross_entropy(logits.t(), lab)) / 2
-    result[1] = 100 * ok.mean()
-    result[2] = 100 * (ok * g).sum() / g.sum()
-    result[3] = 100 * (ok * (1 - g)).sum() / (1 - g).sum()
-    result[4], result[5] = g.sum(), (1 - g).sum()
-
-
-def _double_ssl_bwd(img, txt, scale, scale_p, gt, lse_i, lse_t, gout, grad_scale, scale_grad_scale, Ng, E, r0, Nl, d_img, d_txt, d_scales):
-    with torch.enable_grad():
-        i, t = img.clone().requires_grad_(True), txt.clone().requires_grad_(True)
-        s, sp = scale.clone().requires_grad_(True), scale_p.clone().requires_grad_(True)
-        logits = _ssl_logits(i, t, s, sp, gt)
-        lab = torch.arange(Ng)
-        loss = (torch.nn.functional.cross_entropy(logits, lab) + torch.nn.functional.cross_entropy(logits.t(), lab)) / 2
-        gi, gtx, gs, gp = torch.autograd.grad(loss, (i, t, s, sp))
-    d_img.copy_(gout * grad_scale * gi[r0:r0 + Nl])
-    d_txt.copy_(gout * grad_scale * gtx[r0:r0 + Nl])
-    d_scales[0] += (gout * scale_grad_scale * gs).reshape(())
-    d_scales[1] += (gout * scale_grad_scale * gp).reshape(())
-
-
 def _ssl_worker(rank, world, port, gold, ret):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from lavila_b200 import ops
     from lavila_b200.models.loss import SSLCLIPLoss
-    ops.ssl_clip_loss_fwd, ops.ssl_clip_loss_bwd = _double_ssl_fwd, _double_ssl_bwd
+    from tests import ops_doubles
+    ops.ssl_clip_loss_fwd, ops.ssl_clip_loss_bwd = ops_doubles.ssl_clip_loss_fwd, ops_doubles.ssl_clip_loss_bwd
     r = gold["world2"][rank]
     img, txt = r["image"].clone().requires_grad_(True), r["text"].clone().requires_grad_(True)
     s = torch.tensor(gold["scale"], requires_grad=True)

@@ -78,3 +78,71 @@ def test_full_last_block_and_recompute_paths(monkeypatch):
             if p1.grad is None or float(p1.grad.norm()) < 1e-7 or p1.numel() == 1:
                 continue
             assert rel_l2(p2.grad, p1.grad) < 4e-2, (kw, n1, rel_l2(p2.grad, p1.grad))
+
+
+SSL = torch.load(os.path.join(os.path.dirname(__file__), "golden", "ssl_loss_small.pt"), weights_only=False)
+
+
+@pytest.mark.parametrize("idx", [0, 1, 2, 3])
+def test_sslcliploss_module_host_logic(idx, monkeypatch):
+    """The SSLCLIPLoss module (exp of the pseudo scale, gt handling, result dict, autograd plumbing of both scales) on the doubles,
+    against the unmodified reference: incl. the all-human / all-pseudo cases whose empty class gives a NaN accuracy."""
+    from lavila_b200.models.loss import SSLCLIPLoss
+    ops_doubles.install(monkeypatch)
+    c = SSL["world1"][idx]
+    crit = SSLCLIPLoss(scale_init=SSL["scale_init"])
+    img, txt = c["image"].clone().requires_grad_(True), c["text"].clone().requires_grad_(True)
+    s = torch.tensor(SSL["scale"], requires_grad=True)
+    out = crit({"image_embed": img, "text_embed": txt, "logit_scale": s}, c["gt"])
+    gi, gt, gs, gp = torch.autograd.grad(out["loss"], (img, txt, s, crit.logit_scale_pseudo))
+    torch.testing.assert_close(out["loss"], c["loss"], rtol=1e-5, atol=1e-6)
+    for k in ("clip_acc", "clip_acc_gt", "clip_acc_pseudo"):
+        a, b = float(out[k]), float(c[k])
+        assert (a != a and b != b) or abs(a - b) < 1e-3, (k, a, b)
+    assert torch.equal(out["num_gt"], c["num_gt"]) and torch.equal(out["num_pseudo"], c["num_pseudo"])
+    torch.testing.assert_close(gi, c["grad_image"], rtol=1e-4, atol=1e-7)
+    torch.testing.assert_close(gt, c["grad_text"], rtol=1e-4, atol=1e-7)
+    torch.testing.assert_close(gs, c["grad_scale"], rtol=1e-4, atol=1e-7)
+    torch.testing.assert_close(gp, c["grad_scale_pseudo"], rtol=1e-4, atol=1e-7)
+
+
+def test_clip_hf_host_logic_matches_reference_golden(monkeypatch):
+    """CLIP_HF (video tower / projections / normalise / loss through the engine on the doubles, DistilBERT through the HF module)
+    against the unmodified reference CLIP_HF with the same DistilBERT weights (tests/golden/make_golden_clip_hf.py)."""
+    from transformers import DistilBertConfig, DistilBertModel
+    from lavila_b200.models.loss import CLIPLoss
+    from lavila_b200.models.models import CLIP_HF
+    from lavila_b200.models.timesformer import QuickGELU, SpaceTimeTransformer
+    from tests.golden.make_golden_clip_hf import text_inputs
+    ops_doubles.install(monkeypatch)
+    g = torch.load(os.path.join(os.path.dirname(__file__), "golden", "clip_hf_small.pt"), weights_only=False)
+    cfg = g["cfg"]
+    params = O.init_params(cfg, seed=g["param_seed"])
+    bert = DistilBertModel(DistilBertConfig(**g["bert"])).eval()
+    bert.load_state_dict(g["bert_state"])
+    vis = SpaceTimeTransformer(img_size=cfg["img_size"], patch_size=cfg["patch_size"], embed_dim=cfg["embed_dim"], depth=cfg["depth"],
+                               num_heads=cfg["num_heads"], num_frames=cfg["num_frames"], time_init="zeros", ln_pre=True,
+                               act_layer=QuickGELU)
+    vis.head = torch.nn.Identity()
+    vis.pre_logits = torch.nn.Identity()
+    m = CLIP_HF(embed_dim=cfg["project_dim"], vision_width=cfg["embed_dim"], vision_model=vis, text_width=g["bert"]["dim"],
+                text_model=bert, text_use_cls_token=True, text_is_regressive=False)
+    assert not m.visual.load_state_dict({k[len("visual."):]: v for k, v in params.items() if k.startswith("visual.")},
+                                        strict=False).unexpected_keys
+    with torch.no_grad():
+        m.image_projection.copy_(params["image_projection"])
+        m.text_projection.copy_(g["text_projection"])
+    frames, _ = O.synthetic_batch(cfg, 3, seed=1234)
+    ids, mask = text_inputs()
+    out = m(frames, ids, mask=mask, norm_embed=True)
+    ld = CLIPLoss()(out)
+    ld["loss"].backward()
+    assert rel_l2(out["image_embed"], g["image_embed"]) < 2e-2 and rel_l2(out["text_embed"], g["text_embed"]) < 2e-2
+    assert abs(float(ld["loss"]) - float(g["loss"])) < 3e-2 and abs(float(ld["clip_acc"]) - float(g["clip_acc"])) < 1e-3
+    named = dict(m.named_parameters())
+    for name, want in g["grads"].items():
+        got = named[name].grad
+        if want.numel() == 1:
+            assert abs(float(got) - float(want)) < 0.1 * abs(float(want)) + 1e-3, name
+        else:
+            assert cosine(got, want) > 0.99 and rel_l2(got, want) < 6e-2, "%s: rel_l2 %.3e" % (name, rel_l2(got, want))
