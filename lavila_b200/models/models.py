@@ -37,6 +37,15 @@ class CLIP(nn.Module):
         self.logit_scale = nn.Parameter(torch.ones([]) * np.log(1 / tempearture_init))
         self.initialize_parameters()
 
+    def half(self):
+        """`--use-half` (main_infer_narrator.py:155-156, eval_zeroshot.py:142): a no-op here.  The kernels own the precision
+        (bf16 operands, fp32 accumulation, fp32 parameters / residual stream / softmax -- at least the accuracy of the reference's
+        fp16 module), so the parameters stay fp32 and half-precision inputs are widened on entry."""
+        return self
+
+    def bfloat16(self):
+        return self
+
     def initialize_parameters(self):
         """models.py:115-129."""
         nn.init.normal_(self.token_embedding.weight, std=0.02)
@@ -111,6 +120,15 @@ class CLIP_HF(nn.Module):
         print("=> initialize initial temperature with {}".format(tempearture_init))
         self.logit_scale = nn.Parameter(torch.ones([]) * np.log(1 / tempearture_init))
         self.initialize_parameters()
+
+    def half(self):
+        """`--use-half` (main_infer_narrator.py:155-156, eval_zeroshot.py:142): a no-op here.  The kernels own the precision
+        (bf16 operands, fp32 accumulation, fp32 parameters / residual stream / softmax -- at least the accuracy of the reference's
+        fp16 module), so the parameters stay fp32 and half-precision inputs are widened on entry."""
+        return self
+
+    def bfloat16(self):
+        return self
 
     def initialize_parameters(self):
         """models.py:219-225."""

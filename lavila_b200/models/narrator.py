@@ -26,6 +26,15 @@ class VCLM_HF(nn.Module):
         self.img_attn_pool_norm = LayerNorm(text_width)
         self.initialize_parameters()
 
+    def half(self):
+        """`--use-half` (main_infer_narrator.py:155-156, eval_zeroshot.py:142): a no-op here.  The kernels own the precision
+        (bf16 operands, fp32 accumulation, fp32 parameters / residual stream / softmax -- at least the accuracy of the reference's
+        fp16 module), so the parameters stay fp32 and half-precision inputs are widened on entry."""
+        return self
+
+    def bfloat16(self):
+        return self
+
     def initialize_parameters(self):
         nn.init.normal_(self.img_queries, std=self.text_width ** -0.5)
 

@@ -81,3 +81,13 @@ def test_kv_cached_decoding_host_logic(case, monkeypatch):
         outs.append(m.generate(tok, t, max_text_length=7, top_p=0.95, temperature=0.7, num_return_sequences=2, use_kv_cache=use))
     assert torch.equal(outs[0][0], outs[1][0])
     assert outs[0][0].shape == (4, 7) and outs[0][0].dtype == torch.int64 and bool(torch.isfinite(outs[0][1]).all())
+
+
+def test_use_half_is_accepted(monkeypatch):
+    """main_infer_narrator.py:155-170 `--use-half`: model.half() + half-precision frames must work.  Here the parameters stay fp32
+    (the kernels own the precision) and half inputs are widened on entry: same tokens up to the fp16 rounding of the frames."""
+    c, cfg, m, frames = _setup("small", monkeypatch)
+    ref = m.encode_image(frames)
+    assert m.half() is m and all(p.dtype == torch.float32 for p in m.parameters())
+    tok = m.encode_image(frames.half())
+    assert tok.dtype == torch.float32 and rel_l2(tok, ref) < 5e-3
