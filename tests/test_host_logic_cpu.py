@@ -77,3 +77,34 @@ def test_narrator_factories_exist_with_reference_names():
                  "CLIP_OPENAI_TIMESFORMER_BASE_DISTILBERT_BASE", "CLIP_OPENAI_TIMESFORMER_LARGE_DISTILBERT_BASE",
                  "CLIP_OPENAI_TIMESFORMER_LARGE_336PX_DISTILBERT_BASE"):
         assert callable(getattr(M, name)), name
+
+
+MAIN_PRETRAIN_KWARGS = dict(pretrained=None, pretrained2d=False, text_use_cls_token=False, project_embed_dim=256, gated_xattn=True,
+                            random_init_gpt2=False, timesformer_gated_xattn=True, timesformer_freeze_space=False, freeze_lm_vclm=True,
+                            freeze_visual_vclm=True, freeze_visual_vclm_temporal=False, num_frames=4, drop_path_rate=0.0,
+                            temperature_init=0.07)
+
+
+@pytest.mark.parametrize("name", ["CLIP_OPENAI_TIMESFORMER_BASE", "CLIP_OPENAI_TIMESFORMER_BASE_DISTILBERT_BASE",
+                                  "VCLM_OPENAI_TIMESFORMER_BASE_GPT2"])
+def test_factories_take_the_drivers_keyword_set(name):
+    """main_pretrain.py:157-172 calls every factory with the same 14 keywords; each must accept them all (unknown ones swallowed)
+    and return a model exposing what the driver touches next (:173-176, :199-213)."""
+    import contextlib
+    import io
+    from lavila_b200.models import models as M
+    with contextlib.redirect_stdout(io.StringIO()):
+        model = getattr(M, name)(**MAIN_PRETRAIN_KWARGS)
+    names = [n for n, _ in model.named_parameters()]
+    assert any(n.startswith("visual.blocks.0.timeattn.") for n in names)
+    assert "visual.blocks.0.alpha_timeattn" in names                       # timesformer_gated_xattn=True
+    if name.startswith("CLIP"):
+        assert model.logit_scale.requires_grad and abs(float(model.logit_scale.detach().exp()) - 1 / 0.07) < 1e-3
+    else:
+        # freeze_lm_vclm: only the cross-attention additions of the decoder stay trainable (gpt2_gated.py:1019-1029)
+        dec = dict(model.text_decoder.named_parameters())
+        assert dec["transformer.h.0.crossattention.q_attn.weight"].requires_grad and dec["transformer.h.0.alpha_cattn"].requires_grad
+        assert not dec["transformer.h.0.attn.c_attn.weight"].requires_grad and not dec["transformer.wte.weight"].requires_grad
+        # freeze_visual_vclm: the spatial weights of the video encoder are frozen, the temporal ones are not
+        vis = dict(model.visual.named_parameters())
+        assert not vis["blocks.0.attn.qkv.weight"].requires_grad and vis["blocks.0.timeattn.qkv.weight"].requires_grad
