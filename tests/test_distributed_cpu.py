@@ -139,3 +139,64 @@ def test_sslcliploss_two_rank_host_logic_matches_reference():
     ret = mgr.dict()
     mp.spawn(_ssl_worker, args=(2, 29549, gold, ret), nprocs=2, join=True)
     assert all(ret[r] for r in range(2)), dict(ret)
+
+
+def _install_doubles():
+    from lavila_b200 import engine, ops
+    from tests import ops_doubles
+    for name in ops_doubles.DOUBLES:
+        setattr(ops, name, getattr(ops_doubles, name))
+    engine.SHADOW.clear()
+
+
+def _toy_model_and_batch(batch):
+    from oracle import dual_encoder as O
+    from tests.test_host_schedule_cpu import GOLD, _build
+    cfg = GOLD["norm"]["cfg"]
+    model = _build(cfg, O.init_params(cfg, seed=4), gated=False)
+    frames, text = O.synthetic_batch(cfg, batch, seed=8)
+    return model, frames, text
+
+
+PROBE = ["visual.blocks.0.attn.qkv.weight", "visual.blocks.1.mlp.fc2.bias", "visual.temporal_embed", "visual.cls_token",
+         "transformer.resblocks.0.mlp.c_fc.weight", "token_embedding.weight", "image_projection", "logit_scale"]
+
+
+def _ddp_worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    _install_doubles()
+    from lavila_b200.models.loss import CLIPLoss
+    model, frames, text = _toy_model_and_batch(2 * world)
+    ddp = torch.nn.parallel.DistributedDataParallel(model)
+    crit = CLIPLoss(use_vissl=True, cache_labels=True, rank=rank, world_size=world)
+    sl = slice(2 * rank, 2 * rank + 2)
+    ld = crit(ddp(frames[sl], text[sl], norm_embed=True))
+    ld["loss"].backward()
+    named = dict(model.named_parameters())
+    ret[rank] = {"loss": ld["loss"].detach().clone(), "acc": ld["clip_acc"].detach().clone(),
+                 "grads": {k: named[k].grad.clone() for k in PROBE}}
+    dist.destroy_process_group()
+
+
+def test_ddp_two_ranks_equal_single_process_on_the_global_batch(monkeypatch):
+    """DistributedDataParallel (gloo) around the model + CLIPLoss(use_vissl) on 2 ranks with 2 clips each == one process on the 4
+    clips: same loss / accuracy on every rank, and DDP's averaged parameter gradients equal the single-process gradients (the
+    embedding gradient is scaled by W in the loss, DDP divides by W: SURVEY.md 8(a) a13).  Kernel wrappers = test doubles."""
+    from lavila_b200.models.loss import CLIPLoss
+    from tests import ops_doubles
+    from tests.util import rel_l2
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_ddp_worker, args=(world, 29553, ret), nprocs=world, join=True)
+    ops_doubles.install(monkeypatch)
+    model, frames, text = _toy_model_and_batch(2 * world)
+    ld = CLIPLoss()(model(frames, text, norm_embed=True))
+    ld["loss"].backward()
+    named = dict(model.named_parameters())
+    for r in range(world):
+        assert abs(float(ret[r]["loss"]) - float(ld["loss"])) < 1e-5 and float(ret[r]["acc"]) == float(ld["clip_acc"])
+        for k in PROBE:
+            assert rel_l2(ret[r]["grads"][k], named[k].grad) < 2e-3, (r, k, rel_l2(ret[r]["grads"][k], named[k].grad))
