@@ -171,3 +171,44 @@ def test_training_loop_body_reduces_the_loss(monkeypatch):
         losses.append(float(ld["loss"].detach()))
     assert all(torch.isfinite(torch.tensor(losses)))
     assert losses[-1] < 0.6 * losses[0], losses
+
+
+EDGE_CONFIGS = {
+    "depth1_only_cls_tail": dict(img_size=32, patch_size=16, embed_dim=64, depth=1, num_heads=1, num_frames=2, text_width=64, text_heads=1,
+                                 text_layers=1, context_length=7, vocab_size=64, project_dim=32),
+    "one_frame": dict(img_size=32, patch_size=16, embed_dim=128, depth=2, num_heads=2, num_frames=1, text_width=64, text_heads=1,
+                      text_layers=2, context_length=9, vocab_size=128, project_dim=16),
+    "one_patch_per_frame": dict(img_size=16, patch_size=16, embed_dim=64, depth=2, num_heads=1, num_frames=5, text_width=128, text_heads=2,
+                                text_layers=1, context_length=12, vocab_size=100, project_dim=24),
+    "nine_patches_three_heads": dict(img_size=48, patch_size=16, embed_dim=192, depth=3, num_heads=3, num_frames=3, text_width=192,
+                                     text_heads=3, text_layers=2, context_length=10, vocab_size=90, project_dim=48),
+}
+
+
+@pytest.mark.parametrize("name", list(EDGE_CONFIGS))
+@pytest.mark.parametrize("gated", [False, True])
+def test_host_schedule_edge_geometries_vs_oracle(name, gated, monkeypatch):
+    """Corner geometries (a single block = only the CLS tail; one frame; one patch per frame; 3 heads / 9 patches) against the
+    oracle (itself pinned to the reference): outputs, loss and all gradients."""
+    from lavila_b200.models.loss import CLIPLoss
+    ops_doubles.install(monkeypatch)
+    cfg = dict(EDGE_CONFIGS[name], ln_pre=True)
+    params = O.init_params(cfg, seed=17, gated=gated)
+    model = _build(cfg, params, gated)
+    B = 3
+    frames, text = O.synthetic_batch(cfg, B, seed=23)
+    out = model(frames, text, norm_embed=True)
+    ld = CLIPLoss()(out)
+    ld["loss"].backward()
+    pr = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    ref = O.clip_forward(frames, text, pr, cfg, norm_embed=True)
+    rl = O.clip_loss(ref["image_embed"], ref["text_embed"], ref["logit_scale"])
+    rl["loss"].backward()
+    assert rel_l2(out["image_embed"], ref["image_embed"]) < 2e-2 and rel_l2(out["text_embed"], ref["text_embed"]) < 2e-2
+    assert abs(float(ld["loss"].detach()) - float(rl["loss"].detach())) < 3e-2
+    for n, p in model.named_parameters():
+        want = pr[n].grad
+        if want is None or float(want.norm()) < 1e-7 or want.numel() == 1:
+            continue
+        assert p.grad is not None, n
+        assert cosine(p.grad, want) > 0.99 and rel_l2(p.grad, want) < 8e-2, "%s: rel_l2 %.3e cos %.4f" % (n, rel_l2(p.grad, want), cosine(p.grad, want))
