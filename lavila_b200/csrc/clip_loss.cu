@@ -352,8 +352,9 @@ ssl_clip_loss_bwd_kernel(const float* __restrict__ img, const float* __restrict_
 //            that row (2E floats, peer loads) into the local gathered buffers all_img / all_txt;
 //   phase 2  grid barrier, then exactly the single-GPU loss of clip_loss_fwd_kernel on the gathered rows.
 // NVLink traffic is the minimum (every remote row crosses once); no NCCL call, no gathered staging copy, no host sync.
-// Slot reuse is safe: a rank rewrites slot s two steps later, and every peer has passed DDP's gradient all-reduce of the
-// step in between.  A peer that never publishes (crashed rank) makes the spin time out: result = NaN, no hang.
+// Slot reuse is safe by the flag protocol alone: a rank rewrites slot s in its step s+2 kernel, which starts after its step s+1
+// kernel completed, which needed every peer's step s+1 flag, which a peer only raises after its own step s kernel (the one that
+// reads slot s) has finished.  A peer that never publishes (crashed rank) makes the spin time out: result = NaN, no hang.
 __device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }

@@ -44,8 +44,9 @@ def _peer_exchange(state, B, E, dev):
         return None
     if state.get("xch_unavailable"):
         return None
-    x = state.get("xch")
-    if x is None or x.B != B or x.E != E:
+    pool = state.setdefault("xch_pool", {})       # one exchange per (B, E): train and validation batches may differ
+    x = pool.get((B, E))
+    if x is None:
         import torch.distributed as dist
         from .distributed_utils import PeerEmbeddingExchange
         err = None
@@ -59,9 +60,11 @@ def _peer_exchange(state, B, E, dev):
             if dist.get_rank() == 0:
                 print("lavila_b200: symmetric-memory peer exchange unavailable (%r); CLIPLoss uses one NCCL all_gather" % (err,))
             state["xch_unavailable"] = True
+            pool.clear()
             state["xch"] = None
             return None
-        state["xch"] = x
+        pool[(B, E)] = x
+    state["xch"] = x                               # the exchange used by the latest call (inspected by tools / tests)
     return x
 
 
