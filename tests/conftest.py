@@ -10,6 +10,8 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    config.addinivalue_line("markers", "gpu_fuzz: randomized kernel-vs-test-double sweeps on a CUDA device; NOT part of -m gpu "
+                                       "(run explicitly with -m gpu_fuzz), skipped without a device")
 
 
 def pytest_collection_modifyitems(config, items):
@@ -18,5 +20,5 @@ def pytest_collection_modifyitems(config, items):
         return
     skip = pytest.mark.skip(reason="no CUDA device")
     for item in items:
-        if "gpu" in item.keywords:
+        if "gpu" in item.keywords or "gpu_fuzz" in item.keywords:
             item.add_marker(skip)
