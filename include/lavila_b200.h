@@ -219,11 +219,16 @@ int lv_clip_loss_bwd(const float* img, const float* txt, const float* scale_ptr,
  * word 0 = ready flag]; `step` (> 0, +1 per call on every rank) selects slot step & 1 and is the flag value.  The kernel
  * publishes this rank's rows, pulls every other rank's rows over NVLink into all_img / all_txt [W*Bl, E] (kept for the
  * backward, which is lv_clip_loss_bwd on those buffers) and evaluates the global loss: result[0] = loss, result[1] = acc.
- * ctrl: uint32[4], zeroed once.  Launched cooperatively (W*Bl CTAs must be co-resident).  A peer that never publishes
- * makes the loss NaN after a bounded spin instead of hanging. */
+ * ctrl: uint32[8], zeroed once.  Launched cooperatively: W*Bl CTAs must be co-resident and the [2E + W*Bl] fp32 row buffer
+ * must fit 48 KB -- lv_clip_loss_gather_max_rows(E) returns the largest supported W*Bl on the current device (0 = none), so
+ * the caller can take the all_gather + lv_clip_loss_fwd route for larger global batches instead of failing.
+ * timeout_ms (> 0): how long a CTA waits for a peer's rows (the reference's NCCL gather waits for the process-group
+ * timeout and then raises, distributed_utils.py:56); on expiry the loss is NaN AND ctrl[4] is set to `step` (sticky), which
+ * the caller must check after the stream has drained and turn into an error. */
+int lv_clip_loss_gather_max_rows(int E);
 int lv_clip_loss_fwd_gather(const float* img_local, const float* txt_local, void* const* peers, int rank, int W, int Bl,
                             uint32_t step, float* all_img, float* all_txt, const float* scale_ptr, int E, float* lse_img,
-                            float* lse_txt, float* partial, uint32_t* ctrl, float* result, void* stream);
+                            float* lse_txt, float* partial, uint32_t* ctrl, float* result, int64_t timeout_ms, void* stream);
 
 /* SSLCLIPLoss (lavila/models/loss.py:148-213): gt[i] = 1 human narration / 0 pseudo narration; pair scale
  * c(i,j) = *scale_pseudo_ptr (0 + 0) | sqrt(*scale_pseudo_ptr * *scale_ptr) (0 + 1) | *scale_ptr (1 + 1), both pointers hold the

@@ -374,16 +374,23 @@ __device__ __forceinline__ float ld_relaxed_sys_f32(const float* p) {
   return v;
 }
 
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
 constexpr int P2P_PAD = 32;   // floats after the data of a slot; word 0 = flag
 
 // ctrl[0] = last-CTA counter (as clip_loss_fwd_kernel), ctrl[1] = own-rows-published counter, ctrl[2] = grid-barrier
-// arrivals, ctrl[3] = grid-barrier generation.  All zero before the first call; self-resetting.
+// arrivals, ctrl[3] = grid-barrier generation, ctrl[4] = sticky error word (the step at which a peer's rows did not arrive
+// within timeout_ns; the host raises on it).  All zero before the first call; words 0..3 are self-resetting.
 __global__ void __launch_bounds__(THREADS)
 clip_loss_fwd_gather_kernel(const float* __restrict__ img_local, const float* __restrict__ txt_local,
                             float* const* __restrict__ peers, int rank, int W, int Bl, unsigned int step,
                             float* __restrict__ all_img, float* __restrict__ all_txt, const float* __restrict__ scale_ptr,
                             int E, float* __restrict__ lse_img, float* __restrict__ lse_txt, float* __restrict__ partial,
-                            unsigned int* __restrict__ ctrl, float* __restrict__ result) {
+                            unsigned int* __restrict__ ctrl, float* __restrict__ result, unsigned long long timeout_ns) {
   extern __shared__ float sm[];
   float* a_img = sm;
   float* a_txt = sm + E;
@@ -423,10 +430,18 @@ clip_loss_fwd_gather_kernel(const float* __restrict__ img_local, const float* __
     const float* theirs = peers[owner] + slot_off;
     if (tid == 0) {
       const unsigned int* flag = reinterpret_cast<const unsigned int*>(theirs + (long long)Bl * 2 * E);
-      long long spins = 0;
+      const unsigned long long t0 = globaltimer_ns();
+      unsigned int spins = 0;
       while (ld_acquire_sys(flag) != step) {
-        __nanosleep(200);
-        if (++spins > (1ll << 27)) { timed_out = 1; break; }   // ~30 s: a peer is gone; fail loudly (NaN) instead of hanging
+        __nanosleep(spins < 64 ? 100 : 2000);
+        // the wall-clock bound matches the process group's collective timeout (host passes it): a peer that is merely
+        // slow (checkpoint write, data stall) is waited for like NCCL would; one that is gone fails loudly -- NaN loss
+        // AND the sticky error word the host turns into LavilaB200Error
+        if ((++spins & 1023u) == 0 && globaltimer_ns() - t0 > timeout_ns) {
+          timed_out = 1;
+          atomicExch(ctrl + 4, step);
+          break;
+        }
       }
     }
     __syncthreads();
@@ -566,24 +581,45 @@ extern "C" int lv_ssl_clip_loss_bwd(const float* img, const float* txt, const fl
   return check_launch("lv_ssl_clip_loss_bwd");
 }
 
+static int gather_max_rows(int E) {
+  // co-residency of the cooperative launch and the [2E + Ng] fp32 row buffer (<= 48 KB) both bound Ng = W * Bl
+  long long by_smem = (48 * 1024) / (long long)sizeof(float) - 2ll * E;
+  if (by_smem <= 0) return 0;
+  int per_sm = 0;
+  const size_t smem = (size_t)48 * 1024;     // worst case: occupancy only drops with more shared memory
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, loss::clip_loss_fwd_gather_kernel, loss::THREADS, smem) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  const long long by_occ = (long long)per_sm * sm_count();
+  return (int)(by_occ < by_smem ? by_occ : by_smem);
+}
+
+extern "C" int lv_clip_loss_gather_max_rows(int E) {
+  if (E <= 0 || E % 4 != 0) return 0;
+  return gather_max_rows(E);
+}
+
 extern "C" int lv_clip_loss_fwd_gather(const float* img_local, const float* txt_local, void* const* peers, int rank, int W,
                                        int Bl, uint32_t step, float* all_img, float* all_txt, const float* scale_ptr, int E,
                                        float* lse_img, float* lse_txt, float* partial, uint32_t* ctrl, float* result,
-                                       void* stream) {
+                                       int64_t timeout_ms, void* stream) {
   LV_REQUIRE(img_local && txt_local && peers && all_img && all_txt && scale_ptr && lse_img && lse_txt && partial && ctrl && result,
              "lv_clip_loss_fwd_gather: null pointer");
   LV_REQUIRE(W > 0 && rank >= 0 && rank < W && Bl > 0 && E > 0 && E % 4 == 0 && step > 0, "lv_clip_loss_fwd_gather: bad arguments");
+  LV_REQUIRE(timeout_ms > 0, "lv_clip_loss_fwd_gather: timeout_ms must be positive");
   int Ng = W * Bl;
   const size_t smem = (size_t)(2 * E + Ng) * sizeof(float);
-  LV_REQUIRE(smem <= 48 * 1024, "lv_clip_loss_fwd_gather: Ng=%d too large for one CTA row buffer", Ng);
+  LV_REQUIRE(smem <= 48 * 1024, "lv_clip_loss_fwd_gather: Ng=%d too large for one CTA row buffer (see lv_clip_loss_gather_max_rows)", Ng);
   int per_sm = 0;
   cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, loss::clip_loss_fwd_gather_kernel, loss::THREADS, smem);
   if (e != cudaSuccess) return set_error((int)e, "lv_clip_loss_fwd_gather: occupancy query: %s", cudaGetErrorString(e));
-  LV_REQUIRE((long long)per_sm * sm_count() >= Ng, "lv_clip_loss_fwd_gather: %d CTAs cannot be co-resident (%d per SM)", Ng, per_sm);
+  LV_REQUIRE((long long)per_sm * sm_count() >= Ng, "lv_clip_loss_fwd_gather: %d CTAs cannot be co-resident (%d per SM; see lv_clip_loss_gather_max_rows)", Ng, per_sm);
   float* const* peers_f = reinterpret_cast<float* const*>(peers);
+  unsigned long long timeout_ns = (unsigned long long)timeout_ms * 1000000ull;
   void* args[] = {(void*)&img_local, (void*)&txt_local, (void*)&peers_f, (void*)&rank, (void*)&W, (void*)&Bl, (void*)&step,
                   (void*)&all_img, (void*)&all_txt, (void*)&scale_ptr, (void*)&E, (void*)&lse_img, (void*)&lse_txt,
-                  (void*)&partial, (void*)&ctrl, (void*)&result};
+                  (void*)&partial, (void*)&ctrl, (void*)&result, (void*)&timeout_ns};
   e = cudaLaunchCooperativeKernel((const void*)loss::clip_loss_fwd_gather_kernel, dim3(Ng), dim3(loss::THREADS), args, smem,
                                   (cudaStream_t)stream);
   if (e != cudaSuccess) return set_error((int)e, "lv_clip_loss_fwd_gather: cooperative launch: %s", cudaGetErrorString(e));

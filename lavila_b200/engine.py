@@ -22,8 +22,38 @@ MODE_SPACE, MODE_TIME, MODE_CAUSAL = 0, 1, 2
 
 
 # ----------------------------------------------------------------------------------------------- bf16 weight shadows
+# Derived copies of parameters (bf16 GEMM operands, padded LM head, captured decode graphs) are keyed on
+# (parameter identity, `_version`, PARAM_GENERATION).  `_version` alone is not enough: writes through `param.data`
+# (ZeroRedundancyOptimizer broadcasting the non-owned shards, `main_pretrain.py`'s `logit_scale.data.clamp_`, manual
+# `p.data.copy_()`) do not bump it.  Every optimizer step bumps the generation through a global post-step hook -- the hook
+# of an outer optimizer such as ZeRO fires after its parameter broadcast -- and `invalidate_param_caches()` is the manual
+# switch for any other out-of-band write.  Cost: one cast kernel per weight per step (0.6 ms at TSF-B), which the
+# `_version` change after a normal optimizer step incurs anyway.
+_GEN = [0]
+
+
+def param_generation():
+    return _GEN[0]
+
+
+def invalidate_param_caches(*_a, **_k):
+    """Force every derived parameter copy to be rebuilt at its next use (call after writing through `param.data`)."""
+    _GEN[0] += 1
+
+
+def _install_generation_hook():
+    try:
+        from torch.optim.optimizer import register_optimizer_step_post_hook
+        register_optimizer_step_post_hook(invalidate_param_caches)
+    except Exception:          # pragma: no cover  (very old torch: fall back to re-casting on every forward)
+        _GEN.append("always")
+
+
+_install_generation_hook()
+
+
 class _Shadow:
-    """bf16 copies of fp32 parameters, refreshed when the parameter is modified in place (optimizer step)."""
+    """bf16 copies of fp32 parameters, refreshed when the parameter may have been modified (see above)."""
 
     def __init__(self):
         self._c = {}
@@ -31,8 +61,8 @@ class _Shadow:
     def get(self, p):
         key = id(p)
         ent = self._c.get(key)
-        ver = p._version
-        if ent is None or ent[0] is not p or ent[1] != ver or ent[2].device != p.device:
+        ver = (p._version, _GEN[0])
+        if ent is None or ent[0] is not p or ent[1] != ver or ent[2].device != p.device or len(_GEN) > 1:
             with torch.no_grad():
                 src = p.detach()
                 w = ops.cast_bf16(src.reshape(-1)).view(src.shape)

@@ -103,11 +103,46 @@ class PeerEmbeddingExchange:
         self.handle = symm_mem.rendezvous(self.buf, group)
         self.peers_dev = int(self.handle.buffer_ptrs_dev)
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
-        self.ctrl = torch.zeros(4, device=device, dtype=torch.int32)
+        self.ctrl = torch.zeros(8, device=device, dtype=torch.int32)      # word 4 = sticky peer-timeout flag (clip_loss.cu)
+        self.err_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+        self.err_event = None
         self.step = 0
+        # how long the kernel waits for a peer's rows: the process group's own collective timeout (what the reference's
+        # NCCL all_gather would wait, distributed_utils.py:56), overridable for tests
+        import os
+        t = os.environ.get("LAVILA_B200_P2P_TIMEOUT_S")
+        if t is not None:
+            self.timeout_ms = max(1, int(float(t) * 1000))
+        else:
+            try:
+                self.timeout_ms = max(1000, int(group._get_backend(torch.device(device)).options._timeout.total_seconds() * 1000))
+            except Exception:
+                self.timeout_ms = 600000
         torch.cuda.synchronize(device)
         dist.barrier(group)          # nobody polls a flag before every block is zeroed
 
     def next_step(self):
         self.step += 1
         return self.step
+
+    def post_launch(self):
+        """Enqueue an async D2H copy of the error word behind the kernel (no host sync)."""
+        self.err_host.copy_(self.ctrl[4:5], non_blocking=True)
+        self.err_event = torch.cuda.Event()
+        self.err_event.record()
+
+    def check_error(self, wait=False):
+        """Raise if an earlier fused gather timed out waiting for a peer.  Called before the next launch (by then the
+        training loop's `loss.item()` has drained the stream, so the query is free) and by `CLIPLoss.check_peer_error()`."""
+        if self.err_event is None:
+            return
+        if wait:
+            self.err_event.synchronize()
+        if self.err_event.query():
+            self.err_event = None
+            bad = int(self.err_host[0])
+            if bad:
+                from .._lib import LavilaB200Error
+                raise LavilaB200Error("fused NVLink gather + CLIPLoss: a peer rank did not publish its embeddings within %.0f s "
+                                      "at exchange step %d (rank %d); the loss of that step is NaN"
+                                      % (self.timeout_ms / 1e3, bad, self.rank))

@@ -272,7 +272,8 @@ class GPT2LMHeadModel(nn.Module):
         w = self.lm_head.weight
         V, H = w.shape
         Vp = (V + 3) // 4 * 4
-        key = (w.data_ptr(), w._version, w.device)
+        from ..engine import param_generation
+        key = (w.data_ptr(), w._version, param_generation(), w.device)
         if getattr(self, "_head_key", None) != key:
             wb = torch.zeros(Vp, H, device=w.device, dtype=BF16)
             wb[:V] = SHADOW.get(w)

@@ -36,9 +36,11 @@ def gather_features(image_features, text_features, local_loss=False, gather_with
     return all_image, all_text
 
 
-def _peer_exchange(state, B, E, dev):
+def _peer_exchange(state, B, E, dev, world_size):
     """The symmetric-memory blocks of the fused gather + loss kernel, created on first use (collective).  Disabled with
-    LAVILA_B200_P2P_LOSS=0 (then: one NCCL all_gather + the single-GPU loss kernel)."""
+    LAVILA_B200_P2P_LOSS=0 (then: one NCCL all_gather + the single-GPU loss kernel).  The same NCCL route is taken -- on
+    every rank, agreed BEFORE the symmetric-memory rendezvous -- when the global batch exceeds what the cooperative kernel
+    supports (`lv_clip_loss_gather_max_rows`: ~1184 rows at E = 256 on a B200) or symmetric memory is not importable."""
     import os
     if os.environ.get("LAVILA_B200_P2P_LOSS", "1") == "0" or dev.type != "cuda":
         return None
@@ -47,8 +49,28 @@ def _peer_exchange(state, B, E, dev):
     pool = state.setdefault("xch_pool", {})       # one exchange per (B, E): train and validation batches may differ
     x = pool.get((B, E))
     if x is None:
+        if (B, E) in state.setdefault("xch_too_large", set()):
+            return None
         import torch.distributed as dist
-        from .distributed_utils import PeerEmbeddingExchange
+        # ---- go / no-go, agreed across ranks before anyone enters the (collective, blocking) rendezvous
+        why = None
+        max_rows = ops.clip_loss_gather_max_rows(E)
+        if B * world_size > max_rows:
+            why = "global batch %d > %d rows supported by the cooperative kernel" % (B * world_size, max_rows)
+        else:
+            try:
+                import torch.distributed._symmetric_memory  # noqa: F401
+                from .distributed_utils import PeerEmbeddingExchange
+            except Exception as e:
+                why = "torch symmetric memory unavailable (%r)" % (e,)
+        ok = torch.tensor([0 if why else 1], device=dev, dtype=torch.int32)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 0:
+            if dist.get_rank() == 0:
+                print("lavila_b200: fused NVLink gather not used for B=%d E=%d (%s); CLIPLoss uses one NCCL all_gather"
+                      % (B, E, why or "a peer rank declined"))
+            state["xch_too_large"].add((B, E))
+            return None
         err = None
         try:
             x = PeerEmbeddingExchange(B, E, dev)
@@ -81,13 +103,16 @@ class _ClipLossFn(torch.autograd.Function):
         lse_t = torch.empty(Ng, device=dev, dtype=F32)
         partial = torch.empty(2 * Ng, device=dev, dtype=F32)
         result = torch.empty(2, device=dev, dtype=F32)
-        xch = _peer_exchange(state, B, E, dev) if world_size > 1 else None
+        xch = _peer_exchange(state, B, E, dev, world_size) if world_size > 1 else None
+        state["path"] = "p2p" if xch is not None else ("nccl" if world_size > 1 else "local")
         if xch is not None:
             # ONE kernel: publish own rows -> pull the peers' rows over NVLink -> global loss (csrc/clip_loss.cu)
+            xch.check_error()          # a peer timeout of an earlier step raises here (LavilaB200Error), never silently
             all_i = torch.empty(Ng, E, device=dev, dtype=F32)
             all_t = torch.empty(Ng, E, device=dev, dtype=F32)
             ops.clip_loss_fwd_gather(image, text, xch.peers_dev, rank, world_size, B, xch.next_step(), all_i, all_t, scale, E,
-                                     lse_i, lse_t, partial, xch.ctrl, result)
+                                     lse_i, lse_t, partial, xch.ctrl, result, timeout_ms=xch.timeout_ms)
+            xch.post_launch()
         else:
             if world_size > 1:
                 all_i, all_t = gather_embeddings(image, text, world_size)     # NCCL all_gather (LAVILA_B200_P2P_LOSS=0)
@@ -98,8 +123,9 @@ class _ClipLossFn(torch.autograd.Function):
             ops.clip_loss_fwd(all_i, all_t, scale, Ng, E, lse_i, lse_t, partial, state["counter"], result)
         ctx.saved = (all_i, all_t, scale, lse_i, lse_t)
         ctx.meta = (B, E, Ng, rank, world_size, grad_scale)
-        ctx.mark_non_differentiable(result[1])
-        return result[0], result[1]
+        loss, acc = result[0], result[1]
+        ctx.mark_non_differentiable(acc)           # clip_acc is computed under no_grad in the reference (loss.py:113-116)
+        return loss, acc
 
     @staticmethod
     def backward(ctx, gloss, gacc):
@@ -107,15 +133,16 @@ class _ClipLossFn(torch.autograd.Function):
         ctx.saved = None
         B, E, Ng, rank, world_size, grad_scale = ctx.meta
         dev = all_i.device
-        d_i = torch.empty(Ng, E, device=dev, dtype=F32)
-        d_t = torch.empty(Ng, E, device=dev, dtype=F32)
+        d_i = torch.empty(B, E, device=dev, dtype=F32)
+        d_t = torch.empty(B, E, device=dev, dtype=F32)
         d_s = torch.zeros(1, device=dev, dtype=F32)
         g = gloss.reshape(1).contiguous().float()
-        # all rows: the logit_scale gradient is the full double sum on every rank (as in the reference); the
-        # embedding gradient of this rank is its own slice.
-        ops.clip_loss_bwd(all_i, all_t, scale, lse_i, lse_t, g, grad_scale, 1.0, Ng, E, 0, Ng, d_i, d_t, d_s)
-        sl = slice(rank * B, (rank + 1) * B)
-        return d_i[sl], d_t[sl], d_s.reshape(()), None, None, None, None
+        # Only this rank's B rows are differentiated (2B CTAs instead of 2*W*B).  The logit_scale gradient is the double sum
+        # over (local image rows) x (all texts) times W: the W ranks' shares add up to W x the full sum, and DDP's mean over
+        # ranks (the only way a world_size > 1 gradient is consumed, main_pretrain.py:180) gives exactly the reference's
+        # value, whose ranks each hold the identical full sum (loss.py:78, distributed_utils.py:64-67).
+        ops.clip_loss_bwd(all_i, all_t, scale, lse_i, lse_t, g, grad_scale, float(world_size), Ng, E, rank * B, B, d_i, d_t, d_s)
+        return d_i, d_t, d_s.reshape(()), None, None, None, None
 
 
 class CLIPLoss(nn.Module):
@@ -145,6 +172,18 @@ class CLIPLoss(nn.Module):
         loss, acc = _ClipLossFn.apply(image_features, text_features, logit_scale, self.rank, self.world_size,
                                       grad_scale, self._state)
         return {'loss': loss, 'clip_loss': loss, 'clip_acc': acc}
+
+    @property
+    def gather_path(self):
+        """'p2p' (fused NVLink gather + loss kernel), 'nccl' (all_gather + loss kernel) or 'local' (world size 1): the route
+        the latest forward took."""
+        return self._state.get("path")
+
+    def check_peer_error(self):
+        """Block until the latest fused-gather launch has finished and raise LavilaB200Error if a peer timed out."""
+        x = self._state.get("xch")
+        if x is not None:
+            x.check_error(wait=True)
 
 
 class _SSLClipLossFn(torch.autograd.Function):

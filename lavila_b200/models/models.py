@@ -200,14 +200,33 @@ def get_metric_names(model):
     raise NotImplementedError
 
 
-def _load_checkpoint(model, checkpoint):
+_BENIGN_MISSING = ("attn_mask", "attn.bias", "attn.masked_bias", "position_ids")   # buffers rebuilt by the constructors
+
+
+def _load_checkpoint(model, checkpoint, strict=True):
+    """Reference-format checkpoints are `{'epoch', 'state_dict', 'optimizer', 'scaler', 'best_acc1', 'args'}`
+    (main_pretrain.py:394-402) with `args` an `argparse.Namespace` and `module.`-prefixed keys (DDP).  torch >= 2.6 loads
+    with `weights_only=True` by default, so the Namespace is allow-listed explicitly.  Like the reference's inference drivers
+    (main_infer_narrator.py:107 `load_state_dict(strict=True)`), a key mismatch raises; only re-derivable buffers and a
+    `temporal_embed` of a different length (handled by `inflate_positional_embeds`, eval_zeroshot.py:108-118) are tolerated."""
     if checkpoint is None:
         print("=> no checkpoint given and no network: random initialisation (reference would load OpenAI CLIP weights)")
         return
-    sd = torch.load(checkpoint, map_location='cpu') if isinstance(checkpoint, str) else checkpoint
+    if isinstance(checkpoint, str):
+        import argparse
+        with torch.serialization.safe_globals([argparse.Namespace]):
+            sd = torch.load(checkpoint, map_location='cpu', weights_only=True)
+    else:
+        sd = checkpoint
     sd = sd.get('state_dict', sd)
     sd = {k[len('module.'):] if k.startswith('module.') else k: v for k, v in sd.items()}
-    print(model.load_state_dict(sd, strict=False))
+    res = model.load_state_dict(sd, strict=False)
+    missing = [k for k in res.missing_keys if not any(b in k for b in _BENIGN_MISSING)]
+    unexpected = [k for k in res.unexpected_keys if not any(b in k for b in _BENIGN_MISSING)]
+    if (missing or unexpected) and strict:
+        raise RuntimeError("checkpoint does not match the model: missing %s, unexpected %s" % (missing[:8], unexpected[:8]))
+    print("=> loaded checkpoint: %d tensors, %d benign buffer keys skipped" % (
+        len(sd) - len(res.unexpected_keys), len(res.missing_keys) + len(res.unexpected_keys) - len(missing) - len(unexpected)))
 
 
 def _build(vision_kwargs, vision_width, text_width, text_heads, text_layers, num_frames, timesformer_gated_xattn,

@@ -129,7 +129,8 @@ class VCLM_HF(nn.Module):
         """Persistent buffers of the graph-captured decoding step, keyed by (sequences, max length, device, weight versions):
         per-layer self-attention KV caches, cross-attention K/V buffers (refilled in place for every new batch of clips),
         the static input ids / position scalars and the captured graph.  Weights changing (training) drop the state."""
-        ver = sum(p._version for p in self.text_decoder.parameters())
+        from ..engine import param_generation
+        ver = (sum(p._version for p in self.text_decoder.parameters()), param_generation())
         key = (image_tokens.shape[0], image_tokens.shape[1], max_len, str(image_tokens.device), ver)
         store = self.__dict__.setdefault("_decode_states", {})
         st = store.get(key)

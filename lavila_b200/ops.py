@@ -284,9 +284,15 @@ def ssl_clip_loss_bwd(img, txt, scale, scale_pseudo, gt, lse_img, lse_txt, gout,
 
 
 def clip_loss_fwd_gather(img_local, txt_local, peers_dev_ptr, rank, W, Bl, step, all_img, all_txt, scale, E, lse_img, lse_txt,
-                         partial, ctrl, result):
+                         partial, ctrl, result, timeout_ms=600000):
     """Fused NVLink gather + loss forward (lv_clip_loss_fwd_gather).  peers_dev_ptr: int, device address of the W-pointer array."""
     rc = L.lib().lv_clip_loss_fwd_gather(img_local.data_ptr(), txt_local.data_ptr(), int(peers_dev_ptr), rank, W, Bl, int(step),
                                          all_img.data_ptr(), all_txt.data_ptr(), scale.data_ptr(), E, lse_img.data_ptr(),
-                                         lse_txt.data_ptr(), partial.data_ptr(), ctrl.data_ptr(), result.data_ptr(), _stream())
+                                         lse_txt.data_ptr(), partial.data_ptr(), ctrl.data_ptr(), result.data_ptr(),
+                                         int(timeout_ms), _stream())
     L.check(rc, "lv_clip_loss_fwd_gather")
+
+
+def clip_loss_gather_max_rows(E):
+    """Largest global batch W*B the fused gather + loss kernel supports on the current device (0: not supported)."""
+    return int(L.lib().lv_clip_loss_gather_max_rows(int(E)))

@@ -371,14 +371,15 @@ def clip_loss_fwd(img, txt, scale, Ng, E, lse_i, lse_t, partial, counter, result
 def clip_loss_bwd(img, txt, scale, lse_i, lse_t, gout, grad_scale, scale_grad_scale, Ng, E, r0, Nl, d_img, d_txt, d_scale):
     with torch.enable_grad():
         i, t, s = img.clone().requires_grad_(True), txt.clone().requires_grad_(True), scale.clone().requires_grad_(True)
-        logits = s * i @ t.t()
+        raw = i @ t.t()
+        logits = s * raw
         lab = torch.arange(Ng)
         loss = (torch.nn.functional.cross_entropy(logits, lab) + torch.nn.functional.cross_entropy(logits.t(), lab)) / 2
-        gi, gt, gs = torch.autograd.grad(loss, (i, t, s))
+        gi, gt, gl = torch.autograd.grad(loss, (i, t, logits))
     d_img.copy_(gout * grad_scale * gi[r0:r0 + Nl])
     d_txt.copy_(gout * grad_scale * gt[r0:r0 + Nl])
-    if d_scale is not None:
-        d_scale += gout * scale_grad_scale * gs
+    if d_scale is not None:      # header contract: the double sum over the LOCAL image rows x all texts
+        d_scale += gout * scale_grad_scale * (gl[r0:r0 + Nl] * raw.detach()[r0:r0 + Nl]).sum()
 
 
 def _ssl_logits(img, txt, s, sp, gt):
