@@ -2,7 +2,8 @@
 """Benchmark of the dual-encoder contrastive pre-training step (BASELINE.json metric: clips/sec, TSF-B 16f x 224^2).
 
     python bench.py --gpus N --steps K --warmup W            # our arm (one process per GPU; torchrun for N > 1)
-    python bench.py --impl reference --gpus N --steps K ...   # reference algorithm on the host CPU cores (oracle port)
+    python bench.py --impl reference --gpus N --steps K ...   # the UNMODIFIED reference (baseline/_ref) on the host CPU cores
+    python bench.py --impl eager [--batch B]                  # the UNMODIFIED reference as PyTorch-eager on the B200
 
 One "step" = the body of the reference's train() loop (main_pretrain.py:486-530) on one synthetic batch:
 zero_grad -> model(frames, tokens, norm_embed=True) -> CLIPLoss -> backward -> AdamW.step -> logit_scale clamp.
@@ -11,7 +12,13 @@ zero_grad -> model(frames, tokens, norm_embed=True) -> CLIPLoss -> backward -> A
            read of the loss are inside the timed region.
 `roofline`: tensor-pipe fraction of the dominant kernel family (the tcgen05 GEMM), measured with CUDA events around
            every GEMM launch during extra instrumented steps (same workload), against MEASURED_PEAKS.json.
-`cpu_baseline`: the oracle port (oracle/dual_encoder.py, reference algorithm in fp32 PyTorch) timed on the host cores.
+`block_roofline`: CUDA events around every SpaceTimeBlock forward and backward node (the unit the 0.5x target is defined on).
+`eager_baseline`: the unmodified reference (baseline/_ref: its own factory, CLIP, CLIPLoss, train() body) run as PyTorch-eager
+           under bf16 autocast on the same GPU, in the same process, before our arm (N = 1 only) -- the >= 6x target's denominator.
+`cpu_baseline`: the same reference modules in fp32 on the host cores (kind "reference"); the oracle port only if
+           baseline/_ref is absent (kind "port").
+`loss_check` (N > 1): the fused NVLink gather + loss kernel against the NCCL all_gather route and fp32 torch on the same
+           embeddings, before the timed region; a mismatch above 1e-5 fails the run.
 Prints ONE JSON line on rank 0.
 """
 import argparse
@@ -45,6 +52,9 @@ def parse():
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-eager-baseline", action="store_true")
+    ap.add_argument("--amp", default="bf16", choices=["bf16", "fp16"], help="--impl eager: autocast dtype (fp16 = the "
+                    "reference's literal mode, torch.cuda.amp.autocast + GradScaler, main_pretrain.py:223,490)")
     return ap.parse_args()
 
 
@@ -156,7 +166,11 @@ def run_ours(args):
     if world > 1:
         import datetime
         dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=240))
-    from lavila_b200 import _lib, ops
+    eager = None
+    if rank == 0 and world == 1 and not args.no_eager_baseline and args.model == "base":
+        eager = eager_baseline(args, dev)          # measured first: the reference's eager step needs most of the HBM
+
+    from lavila_b200 import _lib, engine, ops
     from lavila_b200.models import models as M
     from lavila_b200.models.loss import CLIPLoss
 
@@ -217,6 +231,10 @@ def run_ours(args):
     torch.cuda.synchronize()
     assert bool(torch.isfinite(loss)), "non-finite loss in warm-up"
 
+    loss_check = None
+    if world > 1:
+        loss_check = multi_gpu_loss_check(model, crit, frames_d, text_d, rank, world, dev)
+
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
@@ -233,11 +251,33 @@ def run_ours(args):
                "h2d_bytes_per_step": int(frames_h.numel() * 4 + text_h.numel() * 8) * world,
                "d2h_bytes_per_step": 4 * world}
 
-    roof = None
+    roof = block_roof = None
     if not args.no_roofline:
-        # every rank runs the instrumented steps (DDP's gradient all-reduce is collective); rank 0 reports its own GEMMs
+        # every rank runs the instrumented steps (DDP's gradient all-reduce is collective); rank 0 reports its own kernels
         roof = gemm_roofline(lambda: step(frames_d, text_d), ops, torch)
+        block_roof = block_roofline(lambda: step(frames_d, text_d), engine, torch, B, args.frames, flop_kw)
     barrier()
+
+    ddp_exposed = None
+    if world > 1:
+        # step time with and without DDP's gradient all-reduce (no_sync): names the limiter of the 1 -> N curve
+        def step_nosync(fr, tx):
+            with net.no_sync():
+                return step(fr, tx)
+        k = max(2, min(4, args.steps))
+        ms_sync, _, _ = timed(k, host_inputs=False)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            step_nosync(frames_d, text_d)
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        step(frames_d, text_d)        # one synchronised step so every rank's gradients / weights agree again
+        ddp_exposed = {"ms_per_step_sync": round(ms_sync / k, 3), "ms_per_step_no_sync": round(float(t.item()) / k, 3),
+                       "ddp_allreduce_exposed_ms": round((ms_sync - float(t.item())) / k, 3), "steps": k}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline and args.model == "base":
@@ -259,12 +299,24 @@ def run_ours(args):
                        "weights": "random init (no network for checkpoints)",
                        "model_tflop_per_clip": round(fl / 1e12, 4),
                        "model_tflops_achieved": round(value * fl / 1e12 / world, 1)},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
-            "loss": float(loss), "max_mem_gb": round(torch.cuda.max_memory_allocated() / 2 ** 30, 1),
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "block_roofline": block_roof,
+            "cpu_baseline": cpu, "eager_baseline": eager, "loss": float(loss),
+            "max_mem_gb": round(torch.cuda.max_memory_allocated() / 2 ** 30, 1),
         }
+        if eager and eager.get("value"):
+            line["vs_eager"] = {"device_timed": round(value / eager["value"], 3),
+                                "e2e": round(e2e["value"] / eager["value"], 3) if e2e else None,
+                                "note": "ours at batch %d vs the unmodified reference eager at batch %d (clips/s over clips/s)"
+                                        % (B, eager["batch"])}
+        if loss_check is not None:
+            line["loss_check"] = loss_check
+        if ddp_exposed is not None:
+            line["ddp"] = ddp_exposed
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+    if loss_check is not None and not loss_check["ok"]:
+        sys.exit(3)
 
 
 def gemm_roofline(step_fn, ops, torch):
@@ -300,7 +352,8 @@ def gemm_roofline(step_fn, ops, torch):
     ach = tot_fl / (tot_ms / 1e3) / 1e12
     traffic, traffic_note = None, None
     try:   # DRAM bytes per launch from the committed ncu --set full capture of the same kernel (profiles/)
-        t = json.load(open(os.path.join(ROOT, "profiles", "gemm_traffic_r01.json")))
+        cand = sorted(f for f in os.listdir(os.path.join(ROOT, "profiles")) if f.startswith("gemm_traffic_r") and f.endswith(".json"))
+        t = json.load(open(os.path.join(ROOT, "profiles", cand[-1])))
         traffic, traffic_note = t["mean_dram_bytes_per_launch"], t["source"]
     except Exception:
         pass
@@ -310,8 +363,177 @@ def gemm_roofline(step_fn, ops, torch):
             "peak_source": which, "flops_per_step": tot_fl, "gemm_ms_per_step": round(tot_ms, 3)}
 
 
-# --------------------------------------------------------------------------------------------- CPU arms (oracle port)
-def oracle_step_fn(frames):
+
+def block_roofline(step_fn, engine, torch, B, frames, flop_kw):
+    """CUDA events around every SpaceTimeBlock autograd node (forward and backward) of one extra step: the unit
+    BASELINE.json's '>= 0.5x tensor-pipe roofline on SpaceTimeBlock fwd+bwd' is defined on.  FLOPs are the algorithmic
+    3 x F_blk per clip per block for the blocks evaluated in full; the last block (only its CLS row is consumed,
+    LastBlockClsFn skips 62 % of its FLOPs exactly) is timed separately and left out of the fraction."""
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("bf16_tflops_sustained", FALLBACK_PEAK_TFLOPS))
+    rec = {"full": [], "last": []}
+
+    def wrap(cls, name, key):
+        orig = getattr(cls, name)
+
+        def timed(*a, **k):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            r = orig(*a, **k)
+            e1.record()
+            rec[key].append((name, e0, e1))
+            return r
+        setattr(cls, name, staticmethod(timed))
+        return lambda: setattr(cls, name, staticmethod(orig))
+
+    undo = [wrap(engine.SpaceTimeBlockFn, "forward", "full"), wrap(engine.SpaceTimeBlockFn, "backward", "full"),
+            wrap(engine.LastBlockClsFn, "forward", "last"), wrap(engine.LastBlockClsFn, "backward", "last")]
+    try:
+        step_fn()
+        rec["full"].clear()
+        rec["last"].clear()
+        step_fn()
+        torch.cuda.synchronize()
+    finally:
+        for u in undo:
+            u()
+    T, n, D = frames, flop_kw["n"], flop_kw["D"]
+    N = 1 + T * n
+    f_blk = 32 * N * D * D + 4 * D * ((T * n) * (T + n + 2) + 2 * N)
+    nfull = sum(1 for nm, _, _ in rec["full"] if nm == "forward")
+    ms_f = sum(a.elapsed_time(b) for nm, a, b in rec["full"] if nm == "forward")
+    ms_b = sum(a.elapsed_time(b) for nm, a, b in rec["full"] if nm == "backward")
+    ms_last = sum(a.elapsed_time(b) for _, a, b in rec["last"])
+    flops = 3.0 * f_blk * B * nfull
+    ach = flops / max(1e-9, (ms_f + ms_b) / 1e3) / 1e12
+    return {"unit": "TFLOP/s", "blocks_timed": nfull, "flops": flops, "gflop_per_clip_per_block_fwd_bwd": round(3 * f_blk / 1e9, 1),
+            "ms_fwd": round(ms_f, 3), "ms_bwd": round(ms_b, 3), "ms": round(ms_f + ms_b, 3), "achieved": round(ach, 1),
+            "peak": peak, "frac": round(ach / peak, 4), "last_block_cls_only_ms": round(ms_last, 3),
+            "how": "CUDA events around SpaceTimeBlockFn.forward/.backward (engine.py) in one instrumented step"}
+
+
+def multi_gpu_loss_check(model, crit, frames_d, text_d, rank, world, dev):
+    """N > 1 parity of the one thing that differs from N = 1: the fused NVLink gather + CLIPLoss kernel
+    (clip_loss_fwd_gather_kernel).  On the SAME embeddings every rank evaluates (a) the fused path, (b) NCCL all_gather +
+    the single-GPU loss kernel, (c) fp32 torch on the all_gathered batch (loss.py:76-79,107-116 restated inline), and the
+    embedding gradients of (a) against autograd through (c).  Max over ranks; above 1e-5 the bench exits non-zero."""
+    import torch
+    import torch.distributed as dist
+    from lavila_b200.models.loss import CLIPLoss
+    with torch.no_grad():
+        out = model(frames_d, text_d, norm_embed=True)
+    img, txt = out["image_embed"].detach().float(), out["text_embed"].detach().float()
+    scale = out["logit_scale"].detach().float()
+
+    def run(crit_):
+        i, t = img.clone().requires_grad_(True), txt.clone().requires_grad_(True)
+        ld = crit_({"image_embed": i, "text_embed": t, "logit_scale": scale})
+        ld["loss"].backward()
+        return float(ld["loss"]), float(ld["clip_acc"]), i.grad, t.grad
+
+    l_a, acc_a, gi_a, gt_a = run(crit)
+    path = crit.gather_path
+    crit.check_peer_error()
+    os.environ["LAVILA_B200_P2P_LOSS"] = "0"
+    try:
+        nccl_crit = CLIPLoss(use_vissl=True, cache_labels=True, rank=rank, world_size=world)
+        l_b, acc_b, gi_b, gt_b = run(nccl_crit)
+    finally:
+        os.environ["LAVILA_B200_P2P_LOSS"] = "1"
+    # fp32 torch on the concatenated batch
+    both = torch.cat((img, txt), 1).contiguous()
+    buf = [torch.empty_like(both) for _ in range(world)]
+    dist.all_gather(buf, both)
+    allb = torch.cat(buf, 0)
+    E = img.shape[1]
+    B = img.shape[0]
+    ai = allb[:, :E].clone().requires_grad_(True)
+    at = allb[:, E:].clone().requires_grad_(True)
+    logits = (scale * ai) @ at.t()
+    lab = torch.arange(logits.shape[0], device=dev)
+    l_c = (torch.nn.functional.cross_entropy(logits, lab) + torch.nn.functional.cross_entropy(logits.t(), lab)) / 2
+    l_c.backward()
+    acc_c = 100.0 * float((logits.argmax(-1) == lab).float().mean())
+    sl = slice(rank * B, (rank + 1) * B)
+    gi_c, gt_c = world * ai.grad[sl], world * at.grad[sl]          # GatherLayer semantics (distributed_utils.py:64-67)
+    d = torch.tensor([abs(l_a - l_b), abs(l_a - float(l_c)), float((gi_a - gi_b).abs().max()), float((gt_a - gt_b).abs().max()),
+                      float((gi_a - gi_c).abs().max()), float((gt_a - gt_c).abs().max()), abs(acc_a - acc_c)], device=dev)
+    dist.all_reduce(d, op=dist.ReduceOp.MAX)
+    d = [float(x) for x in d]
+    ok = max(d[:6]) <= 1e-5 and d[6] == 0.0 and path == "p2p"
+    return {"path": path, "ok": bool(ok), "loss": l_a, "abs_diff": d[0], "vs_fp32_torch": d[1],
+            "grad_abs_diff_vs_nccl": max(d[2], d[3]), "grad_abs_diff_vs_fp32_torch": max(d[4], d[5]), "acc_diff": d[6],
+            "global_batch": int(logits.shape[0]), "tol": 1e-5}
+
+
+def eager_baseline(args, dev, amp="bf16", steps=4, warmup=2):
+    """The >= 6x target's denominator: the UNMODIFIED reference (baseline/_ref -- its own factory, CLIP, CLIPLoss and the
+    body of train(), main_pretrain.py:486-530) as PyTorch-eager on this GPU.  Batch 64 if it fits, else the largest of
+    (48, 32, 16) that does (torch raises OutOfMemoryError, caught).  Returns None when baseline/_ref is not installed."""
+    import torch
+    from baseline import ref_shim
+    if not ref_shim.available():
+        return {"unavailable": "baseline/_ref not installed (python baseline/install_ref.py needs /root/reference)"}
+    from baseline import ref_arms
+    import contextlib
+    import gc
+    res = None
+    for B in [b for b in (args.batch, 48, 32, 16) if b <= args.batch]:
+        step = None
+        try:
+            with contextlib.redirect_stdout(sys.stderr):
+                step = ref_arms.reference_step_fn(dev, amp=amp, num_frames=args.frames)
+            x, text = make_batch(B, args.frames, 1234)
+            x, text = x.to(dev), text.to(dev)
+            for _ in range(warmup):
+                step(x, text)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                loss = step(x, text)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            res = {"value": round(B / (ms / 1e3), 3), "unit": "clips/s", "batch": B, "ms_per_step": round(ms, 2),
+                   "dtype": "bf16 autocast" if amp == "bf16" else "fp16 autocast + GradScaler", "kind": "reference",
+                   "steps": steps, "warmup": warmup, "loss": float(loss),
+                   "max_mem_gb": round(torch.cuda.max_memory_allocated() / 2 ** 30, 1),
+                   "what": "baseline/_ref lavila.models.models.CLIP_OPENAI_TIMESFORMER_BASE + get_loss (CLIPLoss) + AdamW, "
+                           "train() body of main_pretrain.py:486-530, inputs resident, 1 GPU"}
+        except torch.OutOfMemoryError:
+            res = None
+        finally:
+            del step
+            x = text = None
+            gc.collect()
+            torch.cuda.empty_cache()
+        if res is not None:
+            break
+    torch.cuda.reset_peak_memory_stats()
+    return res if res is not None else {"unavailable": "out of memory at every batch size tried"}
+
+
+# --------------------------------------------------------------------------------------------- CPU arms
+def cpu_step_fn(frames):
+    """(step(batch, seed) -> loss, kind): the unmodified reference on the host cores in fp32 (kind 'reference') when
+    baseline/_ref is installed, else the oracle port of the same algorithm (kind 'port')."""
+    from baseline import ref_shim
+    if ref_shim.available():
+        import contextlib
+        from baseline import ref_arms
+        with contextlib.redirect_stdout(sys.stderr):
+            ref_step = ref_arms.reference_step_fn("cpu", amp="off", num_frames=frames)
+
+        def step(batch, seed):
+            x, text = make_batch(batch, frames, seed)
+            return ref_step(x, text)
+        return step, "reference"
+
     import torch
     from oracle import dual_encoder as O
     cfg = O.tsf_base_config(num_frames=frames)
@@ -327,12 +549,12 @@ def oracle_step_fn(frames):
         opt.step()
         return float(loss)
 
-    return step
+    return step, "port"
 
 
 def host_threads():
-    """Threads the CPU arms may use: scheduler affinity, capped by the cgroup CPU quota and by 32 (the oracle's fp32
-    GEMMs stop scaling past that, and oversubscribing a shared host is catastrophic: 250 s/clip was observed)."""
+    """Threads the CPU arms may use: scheduler affinity, capped by the cgroup CPU quota and by 32 (the fp32 GEMMs stop
+    scaling past that, and oversubscribing a shared host is catastrophic: 250 s/clip was observed)."""
     n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     try:
         q, per = open("/sys/fs/cgroup/cpu.max").read().split()
@@ -347,34 +569,36 @@ def cpu_baseline(frames, budget_s=25.0):
     import torch
     cores = host_threads()
     torch.set_num_threads(cores)
-    step = oracle_step_fn(frames)
+    step, kind = cpu_step_fn(frames)
     t0 = time.time()
-    step(1, 1)                                  # calibrate on one clip (also warms the thread pool)
-    t1 = time.time() - t0
-    batch = int(max(1, min(4, budget_s // max(t1, 1e-3) - 1)))
+    step(2, 1)                                  # calibrate on two clips (the reference cannot train at batch 1: SURVEY B.16)
+    t1 = (time.time() - t0) / 2
+    batch = int(max(2, min(4, budget_s // max(t1, 1e-3) - 1)))
     t0 = time.time()
     step(batch, 2)
     dt = time.time() - t0
-    return {"value": round(batch / dt, 4), "unit": "clips/s", "cores": torch.get_num_threads(), "kind": "port",
-            "sample": "1 fp32 training step (fwd+CLIPLoss+bwd+AdamW) of the oracle port at batch %d, %d frames, after a "
-                      "1-clip calibration step (%.1f s)" % (batch, frames, t1)}
+    what = "the unmodified reference (baseline/_ref)" if kind == "reference" else "the oracle port"
+    return {"value": round(batch / dt, 4), "unit": "clips/s", "cores": torch.get_num_threads(), "kind": kind,
+            "sample": "1 fp32 training step (fwd+CLIPLoss+bwd+AdamW) of %s at batch %d, %d frames, after a "
+                      "2-clip calibration step (%.1f s)" % (what, batch, frames, 2 * t1)}
 
 
 def run_reference(args):
-    """Reference arm: the reference's algorithm (oracle port, fp32 PyTorch on the host cores) on the same config/metric;
-    each step is a bounded sample (small batch) so the whole run ends within minutes.  Rank 0 only."""
+    """Reference arm: the reference's own CPU implementation of the path (baseline/_ref through its public API: factory,
+    CLIP.forward, CLIPLoss, the train() body) in fp32 on the host cores, same metric; each step is a bounded sample (small
+    batch) so the whole run ends within minutes.  Rank 0 only; the other ranks exit without work."""
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
     import torch
     cores = host_threads()
     torch.set_num_threads(cores)
-    step = oracle_step_fn(args.frames)
+    step, kind = cpu_step_fn(args.frames)
     t0 = time.time()
-    step(1, 0)
-    t1 = time.time() - t0
+    step(2, 0)
+    t1 = (time.time() - t0) / 2
     total = args.steps + args.warmup
-    batch = int(max(1, min(4, 150.0 / max(total * t1, 1e-3))))
+    batch = int(max(2, min(4, 150.0 / max(total * t1, 1e-3))))
     for i in range(args.warmup):
         step(batch, 10 + i)
     t0 = time.time()
@@ -388,47 +612,21 @@ def run_reference(args):
             "config": {"workload": "CLIP_OPENAI_TIMESFORMER_BASE dual-encoder pretrain step (fwd + CLIPLoss + bwd + AdamW), "
                                    "%d frames x 224^2; bounded sample: batch %d per step on the host CPU" % (args.frames, batch),
                        "global_batch": batch, "parallelism": "cpu"},
-            "cpu_baseline": {"value": round(v, 4), "unit": "clips/s", "cores": torch.get_num_threads(), "kind": "port",
+            "cpu_baseline": {"value": round(v, 4), "unit": "clips/s", "cores": torch.get_num_threads(), "kind": kind,
                              "sample": "%d steps of batch %d" % (args.steps, batch)},
             "e2e": {"value": round(v, 4), "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
 
 def run_eager(args):
-    """Not part of the driver contract: the oracle port run as PyTorch-eager on the GPU under bf16 autocast -- the
-    'reference PyTorch-eager on 1 B200' baseline of BASELINE.md (B1), since /root/reference cannot travel."""
+    """Not part of the driver contract: the eager_baseline leg on its own (the unmodified reference as PyTorch-eager on one
+    B200, bf16 autocast or --amp fp16 = its literal fp16 + GradScaler mode) -- BASELINE.md B1/B2."""
     import torch
-    from oracle import dual_encoder as O
-    dev = torch.device("cuda", 0)
-    cfg = O.tsf_base_config(num_frames=args.frames)
-    params = {k: v.to(dev).requires_grad_(True) for k, v in O.init_params(cfg, seed=0).items()}
-    opt = torch.optim.AdamW([{"params": list(params.values())}], lr=3e-5, weight_decay=0.01)
-    B = args.batch
-    x, text = make_batch(B, args.frames, 1234)
-    x, text = x.to(dev), text.to(dev)
-
-    def step():
-        opt.zero_grad(set_to_none=True)
-        with torch.autocast("cuda", dtype=torch.bfloat16):
-            out = O.clip_forward(x, text, params, cfg, norm_embed=True)
-            loss = O.clip_loss(out["image_embed"], out["text_embed"], out["logit_scale"])["loss"]
-        loss.backward()
-        opt.step()
-        return loss
-
-    for _ in range(max(2, args.warmup)):
-        step()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        loss = step()
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / args.steps
-    print(json.dumps({"impl": "eager-port", "metric": METRIC, "value": round(B / (ms / 1e3), 3), "unit": "clips/s",
-                      "ms_per_step": round(ms, 2), "batch": B, "dtype": "bf16 autocast", "loss": float(loss),
-                      "max_mem_gb": round(torch.cuda.max_memory_allocated() / 2 ** 30, 1)}))
+    torch.cuda.set_device(0)
+    res = eager_baseline(args, torch.device("cuda", 0), amp=args.amp, steps=max(2, args.steps), warmup=max(2, args.warmup))
+    res = dict(res or {})
+    res.update({"impl": "eager", "metric": METRIC})
+    print(json.dumps(res))
 
 
 if __name__ == "__main__":

@@ -26,8 +26,8 @@ def attn_pool(queries, context, p, prefix, heads, dim_head=64):
     """coca.CrossAttention.forward (coca.py:90-131): pre-LN on queries and context, multi-query K/V (one 64-d head
     shared by all query heads), softmax(sim - amax), no residual.  queries [B, Q, dim], context [B, N, ctx_dim]."""
     B, Q, dim = queries.shape
-    x = F.layer_norm(queries, (dim,), p[prefix + "norm.gamma"], torch.zeros(dim), 1e-5)            # :100
-    c = F.layer_norm(context, (context.shape[-1],), p[prefix + "context_norm.gamma"], torch.zeros(context.shape[-1]), 1e-5)
+    x = F.layer_norm(queries, (dim,), p[prefix + "norm.gamma"], torch.zeros(dim, device=queries.device), 1e-5)            # :100
+    c = F.layer_norm(context, (context.shape[-1],), p[prefix + "context_norm.gamma"], torch.zeros(context.shape[-1], device=context.device), 1e-5)
     q = (x @ p[prefix + "to_q.weight"].t()).reshape(B, Q, heads, dim_head).permute(0, 2, 1, 3)      # :104-105
     q = q * dim_head ** -0.5                                                                        # :108
     k, v = (c @ p[prefix + "to_kv.weight"].t()).chunk(2, dim=-1)                                    # :111  [B, N, 64]
@@ -52,7 +52,7 @@ def gpt2_attention(h, p, prefix, heads, ctx=None):
     w = (q @ k.transpose(-1, -2)) / (dh ** 0.5)                                                    # :207-210
     if ctx is None:
         Lq, Lk = w.shape[-2:]
-        causal = torch.tril(torch.ones(Lk, Lk, dtype=torch.bool))[Lk - Lq:Lk, :Lk]
+        causal = torch.tril(torch.ones(Lk, Lk, dtype=torch.bool, device=h.device))[Lk - Lq:Lk, :Lk]
         w = torch.where(causal, w, torch.tensor(-1e4))                                             # :216-220
     a = torch.softmax(w, dim=-1) @ v                                                               # :226-238
     a = a.permute(0, 2, 1, 3).reshape(B, L, H)
@@ -96,7 +96,7 @@ def vclm_encode_image(image_bcthw, p, cfg):
     q = p["img_queries"].unsqueeze(0).expand(B, -1, -1)                                            # :84
     q = attn_pool(q, x, p, "img_attn_pool.", cfg["pool_heads"])                                    # :85
     W = q.shape[-1]
-    return F.layer_norm(q, (W,), p["img_attn_pool_norm.gamma"], torch.zeros(W), 1e-5)              # :86
+    return F.layer_norm(q, (W,), p["img_attn_pool_norm.gamma"], torch.zeros(W, device=q.device), 1e-5)              # :86
 
 
 def vclm_forward(image, text, p, cfg):

@@ -200,3 +200,79 @@ def test_ddp_two_ranks_equal_single_process_on_the_global_batch(monkeypatch):
         assert abs(float(ret[r]["loss"]) - float(ld["loss"])) < 1e-5 and float(ret[r]["acc"]) == float(ld["clip_acc"])
         for k in PROBE:
             assert rel_l2(ret[r]["grads"][k], named[k].grad) < 2e-3, (r, k, rel_l2(ret[r]["grads"][k], named[k].grad))
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# ZeroRedundancyOptimizer (main_pretrain.py:215-219, the TSF-L@HR recipe): after its step every rank holds updated
+# weights it did NOT step itself -- they arrive by a broadcast into `param.data`, which does not bump `param._version`.  The bf16
+# GEMM-operand shadows (engine.SHADOW) must follow them: they are keyed on the optimizer-step generation too.
+def _zero_worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    _install_doubles()
+    from torch.distributed.optim import ZeroRedundancyOptimizer
+    from lavila_b200 import engine
+    from lavila_b200.models.loss import CLIPLoss
+    model, frames, text = _toy_model_and_batch(2 * world)
+    ddp = torch.nn.parallel.DistributedDataParallel(model)
+    crit = CLIPLoss(use_vissl=True, cache_labels=True, rank=rank, world_size=world)
+    opt = ZeroRedundancyOptimizer(model.parameters(), optimizer_class=torch.optim.AdamW, lr=1e-2, weight_decay=0.01)
+    sl = slice(2 * rank, 2 * rank + 2)
+    losses, stale = [], 0
+    for it in range(3):
+        ld = crit(ddp(frames[sl], text[sl], norm_embed=True))
+        opt.zero_grad(set_to_none=True)
+        ld["loss"].backward()
+        opt.step()
+        losses.append(float(ld["loss"]))
+        for n, p in model.named_parameters():
+            if p.ndim == 2 and "weight" in n:               # the GEMM weights are the shadowed ones
+                if not torch.equal(engine.SHADOW.get(p).float(), p.detach().to(torch.bfloat16).float()):
+                    stale += 1
+    # all ranks hold identical weights after ZeRO's broadcast
+    flat = torch.cat([p.detach().flatten() for p in model.parameters()])
+    other = [torch.empty_like(flat) for _ in range(world)]
+    dist.all_gather(other, flat)
+    ret[rank] = {"losses": losses, "stale": stale, "same": bool(all(torch.equal(o, flat) for o in other))}
+    dist.destroy_process_group()
+
+
+def test_zero_redundancy_optimizer_two_ranks_refreshes_the_bf16_shadows():
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_zero_worker, args=(world, 29557, ret), nprocs=world, join=True)
+    for r in range(world):
+        assert ret[r]["stale"] == 0, dict(ret)
+        assert ret[r]["same"]
+        assert ret[r]["losses"][-1] < ret[r]["losses"][0], ret[r]["losses"]        # and it trains
+    assert ret[0]["losses"] == ret[1]["losses"]
+
+
+def test_shadow_follows_param_data_writes_after_invalidate(monkeypatch):
+    from lavila_b200 import engine
+    from tests import ops_doubles
+    ops_doubles.install(monkeypatch)
+    p = torch.nn.Parameter(torch.randn(8, 8))
+    a = engine.SHADOW.get(p).clone()
+    p.data.add_(1.0)                               # does not bump p._version
+    engine.invalidate_param_caches()
+    b = engine.SHADOW.get(p)
+    assert not torch.equal(a, b) and torch.equal(b.float(), p.detach().to(torch.bfloat16).float())
+    opt = torch.optim.SGD([p], lr=0.5)
+    p.grad = torch.ones_like(p)
+    g0 = engine.param_generation()
+    opt.step()
+    assert engine.param_generation() > g0          # the global post-step hook
+    assert torch.equal(engine.SHADOW.get(p).float(), p.detach().to(torch.bfloat16).float())
+
+
+def test_clip_acc_carries_no_graph(monkeypatch):
+    from lavila_b200.models.loss import CLIPLoss
+    from tests import ops_doubles
+    ops_doubles.install(monkeypatch)
+    i = torch.nn.functional.normalize(torch.randn(4, 8), dim=-1).requires_grad_(True)
+    t = torch.nn.functional.normalize(torch.randn(4, 8), dim=-1).requires_grad_(True)
+    ld = CLIPLoss()({"image_embed": i, "text_embed": t, "logit_scale": torch.tensor(14.0)})
+    assert ld["loss"].requires_grad and not ld["clip_acc"].requires_grad and ld["clip_acc"].grad_fn is None

@@ -1,0 +1,108 @@
+"""Value parity at the REAL geometries, the oracle run in fp32 on the same GPU:
+
+* BASELINE config 2's model -- CLIP_OPENAI_TIMESFORMER_BASE: TSF-B depth 12, 16 frames x 224^2, text tower 512 / 8 heads /
+  12 layers / context 77 / vocab 49 408 -- forward, CLIPLoss and backward at batch 3 (B*N = 9411 rows: not a multiple of
+  any GEMM tile, so edge tiles are exercised), against oracle/dual_encoder.py (pinned to the unmodified reference by
+  tests/test_oracle.py).  Tolerances (bf16 operands / fp32 accumulation vs fp32): embeddings rel-L2 <= 2e-2, loss
+  |diff| <= 3e-2, a 512-entry sample of every parameter gradient rel-L2 <= 6e-2 (cosine >= 0.99).
+* The narrator at GPT-2 XL width (n_embd 1600, 25 heads, 256 image queries, TSF-L/14-width 1024 visual tokens, 4 decoder
+  layers with cross-attention every 2nd) against oracle/narrator.py: image tokens and teacher-forced logits.
+"""
+import pytest
+import torch
+
+from oracle import dual_encoder as O
+from oracle import narrator as ON
+from tests.util import assert_close_bf16, cosine, rel_l2
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _sample(numel, k=512, seed=7):
+    g = torch.Generator().manual_seed(seed + numel)
+    return torch.randint(0, numel, (k,), generator=g)
+
+
+def test_tsf_base_full_depth_batch3_vs_fp32_oracle():
+    from lavila_b200.models.loss import CLIPLoss
+    from tests.test_gpu_model import build_clip
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    cfg = O.tsf_base_config(num_frames=16)
+    params = O.init_params(cfg, seed=2, gated=True)
+    B = 3
+    frames, text = O.synthetic_batch(cfg, B, seed=4321)
+    model = build_clip(cfg, params, gated=True)
+    out = model(frames.to(DEV), text.to(DEV), norm_embed=True)
+    ld = CLIPLoss()(out)
+    ld["loss"].backward()
+    torch.cuda.synchronize()
+    # the oracle: same parameters / inputs, fp32, same device
+    pr = {k: v.to(DEV).clone().requires_grad_(True) for k, v in params.items()}
+    ref = O.clip_forward(frames.to(DEV), text.to(DEV), pr, cfg, norm_embed=True)
+    rl = O.clip_loss(ref["image_embed"], ref["text_embed"], ref["logit_scale"])
+    rl["loss"].backward()
+    assert_close_bf16(out["image_embed"], ref["image_embed"], "image_embed (depth 12)", rel=2e-2)
+    assert_close_bf16(out["text_embed"], ref["text_embed"], "text_embed (W=512, 8 heads, L=77, 12 layers)", rel=2e-2)
+    assert abs(float(ld["loss"]) - float(rl["loss"])) <= 3e-2, (float(ld["loss"]), float(rl["loss"]))
+    assert float(ld["clip_acc"]) == float(rl["clip_acc"])
+    worst = (0.0, None)
+    for name, p in model.named_parameters():
+        g, gr = p.grad, pr[name].grad
+        assert g is not None, name
+        if float(gr.norm()) < 1e-9:
+            continue
+        if g.numel() > 4096:
+            idx = _sample(g.numel()).to(DEV)
+            got, want = g.flatten()[idx], gr.flatten()[idx]
+        else:
+            got, want = g.flatten(), gr.flatten()
+        r, c = rel_l2(got, want), cosine(got, want)
+        if g.numel() == 1:
+            # scalars (logit_scale, the 12 tanh gates): sums of signed terms over B*N*D entries; sign and magnitude
+            assert c > 0.99 and r < 1e-1, "%s: rel_l2 %.3e" % (name, r)
+            continue
+        if r > worst[0]:
+            worst = (r, name)
+        assert c >= 0.99 and r <= 6e-2, "%s: rel_l2 %.3e cosine %.5f" % (name, r, c)
+    print("full-depth TSF-B: worst gradient rel_l2 %.3e (%s)" % worst)
+
+
+XL_WIDTH = dict(
+    visual=dict(img_size=56, patch_size=14, embed_dim=1024, depth=2, num_heads=16, num_frames=4, ln_pre=True),
+    n_embd=1600, n_head=25, n_layer=4, cross_attn_freq=2, vocab_size=50257, n_positions=77, num_img_queries=256, pool_heads=25)
+
+
+def test_narrator_gpt2_xl_width_vs_fp32_oracle():
+    """VCLM_OPENAI_TIMESFORMER_LARGE_GPT2_XL's widths (lavila/models/models.py:1021-1070): ln_fwd_generic at D = 1600, 25-head
+    cross / self attention, the 256-query multi-query pool over 1024-wide visual tokens, the 50 257-row LM head."""
+    from tests.test_gpu_narrator import build
+    torch.backends.cuda.matmul.allow_tf32 = False
+    cfg = XL_WIDTH
+    p = ON.init_narrator_params(cfg, seed=1)
+    m = build(cfg, p)
+    vcfg = dict(cfg["visual"], context_length=8, vocab_size=8)
+    frames, _ = O.synthetic_batch(vcfg, 2, seed=31)
+    g = torch.Generator().manual_seed(5)
+    text = torch.randint(0, cfg["vocab_size"], (2, 21), generator=g)
+    with torch.no_grad():
+        tok = m.encode_image(frames.to(DEV))
+        out = m(frames.to(DEV), text.to(DEV))
+        pd = {k: v.to(DEV) for k, v in p.items()}
+        tok_ref = ON.vclm_encode_image(frames.to(DEV), pd, cfg)
+        ref = ON.vclm_forward(frames.to(DEV), text.to(DEV), pd, cfg)
+    assert_close_bf16(tok, tok_ref, "image tokens (256 queries x 1600)", rel=2e-2)
+    assert torch.equal(out["labels"], ref["labels"])
+    assert_close_bf16(out["text_tokens_logits"], ref["text_tokens_logits"], "teacher-forced logits (XL width)", rel=3e-2, cos=0.999)
+    # KV-cached incremental decoding == full prefix at this width too
+    ids = text[:, :6].contiguous().to(DEV)
+    with torch.no_grad():
+        full = m.text_decoder(ids, encoder_hidden_states=tok).logits
+        cache, ctx = {"max_len": 8}, {}
+        got = [m.text_decoder(ids[:, :3].contiguous(), encoder_hidden_states=tok, ctx_kv_cache=ctx, self_kv_cache=cache, past_len=0).logits]
+        for t in range(3, 6):
+            got.append(m.text_decoder(ids[:, t:t + 1].contiguous(), encoder_hidden_states=tok, ctx_kv_cache=ctx,
+                                      self_kv_cache=cache, past_len=t).logits)
+    # prefill (tcgen05 GEMM) and single-position steps (skinny split-K GEMM) sum in different orders
+    assert rel_l2(torch.cat(got, 1), full) < 5e-3
