@@ -10,8 +10,7 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
-    config.addinivalue_line("markers", "gpu_fuzz: randomized kernel-vs-test-double sweeps on a CUDA device; NOT part of -m gpu "
-                                       "(run explicitly with -m gpu_fuzz), skipped without a device")
+    config.addinivalue_line("markers", "gpu_fuzz: seeded kernel-vs-test-double sweeps on a CUDA device (also carry the gpu marker)")
 
 
 def pytest_collection_modifyitems(config, items):

@@ -3,8 +3,7 @@ same arguments, on the device (kernel) and on CPU copies (double); every output 
 pinned to the unmodified reference through the host-logic CPU tests, so this closes the loop per entry point over many more shapes,
 strides and flag combinations than the hand-written parity tests.
 
-NOT selected by `-m gpu` (the marker is `gpu_fuzz`): run it on a B200 with
-    python -m pytest tests/test_gpu_fuzz_vs_doubles.py -m gpu_fuzz -q
+Fixed seeds; part of `-m gpu` since round 2 (also selectable alone with `-m gpu_fuzz`).
 """
 import random
 
@@ -14,7 +13,7 @@ import torch
 from tests import ops_doubles as D
 from tests.util import cosine, rel_l2
 
-pytestmark = pytest.mark.gpu_fuzz
+pytestmark = [pytest.mark.gpu, pytest.mark.gpu_fuzz]
 DEV = "cuda"
 BF16, F32 = torch.bfloat16, torch.float32
 
@@ -56,6 +55,8 @@ def test_gemm_fuzz(seed):
     N = rng.choice([64, 128, 256, 320, 768])
     K = rng.choice([64, 128, 192, 768])
     a_mn, b_mn = rng.choice([(0, 0), (0, 1), (1, 1)])
+    if a_mn and M % 8:
+        M = (M + 7) // 8 * 8          # an MN-major A has row pitch M: TMA needs a 16-byte multiple
     torch.manual_seed(seed)
     A = (torch.randn((K, M) if a_mn else (M, K), device=DEV) * 0.5).to(BF16)
     Bm = (torch.randn((K, N) if b_mn else (N, K), device=DEV) * 0.1).to(BF16)
@@ -151,10 +152,11 @@ def test_flash_and_skinny_fuzz(seed):
     causal = rng.choice([False, True]) and Lq <= Lk
     torch.manual_seed(seed)
     q = torch.randn(B * Lq, H * 64, device=DEV).to(BF16)
-    kv = torch.randn(B * Lk, 2 * H * 64, device=DEV).to(BF16)
+    k = torch.randn(B * Lk, H * 64, device=DEV).to(BF16)
+    v = torch.randn(B * Lk, H * 64, device=DEV).to(BF16)
     out = torch.zeros(B * Lq, H * 64, device=DEV, dtype=BF16)
-    pairs = _both("flash_attn_fwd", [q, kv, kv[:, H * 64:], out, B, H, Lq, Lk],
-                  dict(q_rows=Lq, kv_rows=Lk, ld_q=H * 64, ld_kv=2 * H * 64, ld_out=H * 64, causal=causal))
+    pairs = _both("flash_attn_fwd", [q, k, v, out, B, H, Lq, Lk],
+                  dict(q_rows=Lq, kv_rows=Lk, ld_q=H * 64, ld_kv=H * 64, ld_out=H * 64, causal=causal))
     for dev_t, cpu_t in pairs:
         if dev_t is out:
             _cmp(dev_t, cpu_t, "flash B%d H%d Lq%d Lk%d causal=%s" % (B, H, Lq, Lk, causal))

@@ -4,7 +4,8 @@
   12 layers / context 77 / vocab 49 408 -- forward, CLIPLoss and backward at batch 3 (B*N = 9411 rows: not a multiple of
   any GEMM tile, so edge tiles are exercised), against oracle/dual_encoder.py (pinned to the unmodified reference by
   tests/test_oracle.py).  Tolerances (bf16 operands / fp32 accumulation vs fp32): embeddings rel-L2 <= 2e-2, loss
-  |diff| <= 3e-2, a 512-entry sample of every parameter gradient rel-L2 <= 6e-2 (cosine >= 0.99).
+  |diff| <= 3e-2, EVERY parameter gradient in full rel-L2 <= 6e-2 and cosine >= 0.998 (measured r02: all <= 3.0e-2 except
+  ln_final.bias 4.3e-2; a 512-entry sample is a noisier statistic -- pos_embed's gradient is dominated by its CLS row).
 * The narrator at GPT-2 XL width (n_embd 1600, 25 heads, 256 image queries, TSF-L/14-width 1024 visual tokens, 4 decoder
   layers with cross-attention every 2nd) against oracle/narrator.py: image tokens and teacher-forced logits.
 """
@@ -17,11 +18,6 @@ from tests.util import assert_close_bf16, cosine, rel_l2
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
-
-
-def _sample(numel, k=512, seed=7):
-    g = torch.Generator().manual_seed(seed + numel)
-    return torch.randint(0, numel, (k,), generator=g)
 
 
 def test_tsf_base_full_depth_batch3_vs_fp32_oracle():
@@ -46,18 +42,14 @@ def test_tsf_base_full_depth_batch3_vs_fp32_oracle():
     assert_close_bf16(out["image_embed"], ref["image_embed"], "image_embed (depth 12)", rel=2e-2)
     assert_close_bf16(out["text_embed"], ref["text_embed"], "text_embed (W=512, 8 heads, L=77, 12 layers)", rel=2e-2)
     assert abs(float(ld["loss"]) - float(rl["loss"])) <= 3e-2, (float(ld["loss"]), float(rl["loss"]))
-    assert float(ld["clip_acc"]) == float(rl["clip_acc"])
+    assert abs(float(ld["clip_acc"]) - float(rl["clip_acc"])) < 1e-3          # same arg-max decisions (100 * k / B)
     worst = (0.0, None)
     for name, p in model.named_parameters():
         g, gr = p.grad, pr[name].grad
         assert g is not None, name
         if float(gr.norm()) < 1e-9:
             continue
-        if g.numel() > 4096:
-            idx = _sample(g.numel()).to(DEV)
-            got, want = g.flatten()[idx], gr.flatten()[idx]
-        else:
-            got, want = g.flatten(), gr.flatten()
+        got, want = g.flatten(), gr.flatten()
         r, c = rel_l2(got, want), cosine(got, want)
         if g.numel() == 1:
             # scalars (logit_scale, the 12 tanh gates): sums of signed terms over B*N*D entries; sign and magnitude
@@ -65,7 +57,7 @@ def test_tsf_base_full_depth_batch3_vs_fp32_oracle():
             continue
         if r > worst[0]:
             worst = (r, name)
-        assert c >= 0.99 and r <= 6e-2, "%s: rel_l2 %.3e cosine %.5f" % (name, r, c)
+        assert c >= 0.998 and r <= 6e-2, "%s: rel_l2 %.3e cosine %.5f" % (name, r, c)
     print("full-depth TSF-B: worst gradient rel_l2 %.3e (%s)" % worst)
 
 
