@@ -243,13 +243,13 @@ space_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const Param
         if ((cc + 1) * 32 <= Lk) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            pv[j] = exp2f(fmaf(__uint_as_float(r[j]), sl2, -mb));
+            pv[j] = ex2_fast(fmaf(__uint_as_float(r[j]), sl2, -mb));
             sum += pv[j];
           }
         } else {
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            pv[j] = (cc * 32 + j < Lk) ? exp2f(fmaf(__uint_as_float(r[j]), sl2, -mb)) : 0.f;
+            pv[j] = (cc * 32 + j < Lk) ? ex2_fast(fmaf(__uint_as_float(r[j]), sl2, -mb)) : 0.f;
             sum += pv[j];
           }
         }
@@ -269,7 +269,7 @@ space_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const Param
         float pv[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          pv[j] = (192 + j < Lk) ? exp2f(fmaf(__uint_as_float(r[j]), sl2, -mb)) : 0.f;
+          pv[j] = (192 + j < Lk) ? ex2_fast(fmaf(__uint_as_float(r[j]), sl2, -mb)) : 0.f;
           sum += pv[j];
         }
         const uint32_t atom = p_tile + 3 * 16384;
@@ -542,6 +542,10 @@ space_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __gri
       if (has_next) {
         cn = decode(p, gn);
         issue_kv(it + 1, cn);   // buffers of group it-1's Q / dO: free since bar_free(it-1)
+        if (lane == 0) {        // Q / dO of the next group can only land once this group's MMAs are done: pull them into L2 now
+          tma_prefetch_2d(&tm_qkv, cn.h * HD, (int)cn.base_row);
+          tma_prefetch_2d(&tm_do, cn.h * HD, (int)cn.base_row);
+        }
         prep(it + 1, cn);
       }
       if (lane == 0) mbar_wait(bar_free, it & 1);   // every MMA of group `it` has read its operands
@@ -663,8 +667,18 @@ space_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __gri
         const int ncols = qt ? 40 : 64;         // this warp's share of the query columns
         const int col_base = hf * ncols;
         const uint32_t pt_row = pt_tile + row * 128, ds_row = ds_tile + row * 128;
+        // Key tile 1 holds keys 128 .. n: warps whose 32 key rows are all past the CLS key (warp-uniform) only clear their
+        // rows of the staged tiles -- no TMEM traffic, no exponentials.
+        const bool warp_all_masked = kt * 128 + q * 32 >= Lk;
+        if (warp_all_masked) {
+          for (int c8 = col_base; c8 < col_base + ncols; c8 += 8) {
+            const uint32_t off = (c8 >> 6) * 16384 + ((((c8 & 63) >> 3) ^ (row & 7)) << 4);
+            st_shared_v4(pt_row + off, 0, 0, 0, 0);
+            st_shared_v4(ds_row + off, 0, 0, 0, 0);
+          }
+        }
         // 32 columns per TMEM round trip (one wait per 32x2 values instead of per 8)
-        for (int cb = 0; cb < ncols; cb += 32) {
+        for (int cb = 0; cb < (warp_all_masked ? 0 : ncols); cb += 32) {
           const int col0 = col_base + cb;       // query column inside the tile
           uint32_t s32[32], d32[32];
           const bool wide = cb + 32 <= ncols;   // qt = 1 ends with an 8-column remainder (40 = 32 + 8)
@@ -690,10 +704,13 @@ space_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __gri
               const float l8[8] = {la.x, la.y, la.z, la.w, lb.x, lb.y, lb.z, lb.w};
               const float dl8[8] = {da.x, da.y, da.z, da.w, db.x, db.y, db.z, db.w};
               float pv[8], dv[8];
-              if (key_ok && qg + 8 <= Lq) {     // interior: no masking
+              if (!key_ok) {                    // key row past the CLS key: zeros (rows of a partly valid warp)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { pv[j] = 0.f; dv[j] = 0.f; }
+              } else if (qg + 8 <= Lq) {        // interior: no masking
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                  const float pj = exp2f(fmaf(__uint_as_float(s32[g8 * 8 + j]), sl2, -l8[j]));
+                  const float pj = ex2_fast(fmaf(__uint_as_float(s32[g8 * 8 + j]), sl2, -l8[j]));
                   pv[j] = pj;
                   dv[j] = pj * (__uint_as_float(d32[g8 * 8 + j]) - dl8[j]) * p.scale;
                 }
@@ -701,7 +718,7 @@ space_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __gri
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                   const bool ok = key_ok && (qg + j < Lq);
-                  const float pj = ok ? exp2f(fmaf(__uint_as_float(s32[g8 * 8 + j]), sl2, -l8[j])) : 0.f;
+                  const float pj = ok ? ex2_fast(fmaf(__uint_as_float(s32[g8 * 8 + j]), sl2, -l8[j])) : 0.f;
                   pv[j] = pj;
                   dv[j] = ok ? pj * (__uint_as_float(d32[g8 * 8 + j]) - dl8[j]) * p.scale : 0.f;
                 }

@@ -13,6 +13,9 @@ constexpr int EPI_PITCH = 16;  // floats: a 32-row x 16-column half chunk per wa
 struct Args {
   int M, N, K;
   int num_m_blks, num_n_blks, k_splits, kb_per_split, num_kb;
+  // stream-K (split-K GEMMs with the atomic epilogue): the tiles x k-blocks iteration space is cut into one contiguous,
+  // equally long span per CTA (pair); a span covers the tail of one tile and the head of the next.  0 = classic split-K.
+  long long sk_total_kb, sk_kb_per_cta;
   int flags;
   void* out;
   long long ldo;
@@ -34,6 +37,43 @@ __device__ __forceinline__ float sigmoidf_fast(float x) {
   return fmaf(0.5f, t, 0.5f);
 }
 
+
+// Work items of one CTA (pair): (tile, k-block range).  Every warp role walks the same sequence.
+struct ItemIter {
+  bool streamk;
+  int item, stride, total_items, n_tiles, kb_per_split, num_kb;
+  long long gk, g1;
+  __device__ __forceinline__ ItemIter(const Args& g, int cta_id, int num_ctas) {
+    streamk = g.sk_kb_per_cta > 0;
+    n_tiles = g.num_m_blks * g.num_n_blks;
+    num_kb = g.num_kb;
+    kb_per_split = g.kb_per_split;
+    item = cta_id;
+    stride = num_ctas;
+    total_items = n_tiles * g.k_splits;
+    gk = (long long)cta_id * g.sk_kb_per_cta;
+    g1 = gk + g.sk_kb_per_cta;
+    if (g1 > g.sk_total_kb) g1 = g.sk_total_kb;
+  }
+  __device__ __forceinline__ bool next(int& tile, int& kb0, int& kb1) {
+    if (streamk) {
+      if (gk >= g1) return false;
+      tile = (int)(gk / num_kb);
+      kb0 = (int)(gk - (long long)tile * num_kb);
+      const long long left = g1 - gk;
+      kb1 = (left < (long long)(num_kb - kb0)) ? kb0 + (int)left : num_kb;
+      gk += kb1 - kb0;
+      return true;
+    }
+    if (item >= total_items) return false;
+    const int split = item / n_tiles;
+    tile = item - split * n_tiles;
+    kb0 = split * kb_per_split;
+    kb1 = min(num_kb, kb0 + kb_per_split);
+    item += stride;
+    return true;
+  }
+};
 
 // Flag sets with a dedicated compile-time specialisation (everything else runs the runtime-flag kernel).
 __host__ __device__ constexpr bool is_specialised(int a_mn, int b_mn, int f) {
@@ -160,7 +200,7 @@ __device__ __forceinline__ void epilogue_tile(const Args& g, const int flags, co
           }
           if (flags & LV_EPI_ATOMIC) {
             float* o = reinterpret_cast<float*>(g.out) + (long long)m * g.ldo + n;
-            red_add_f32(o, v.x); red_add_f32(o + 1, v.y); red_add_f32(o + 2, v.z); red_add_f32(o + 3, v.w);
+            red_add_v4_f32(o, v);          // one 16-byte vector reduction (n and ldo are multiples of 4)
           } else if (flags & LV_EPI_OUT_F32) {
             *reinterpret_cast<float4*>(reinterpret_cast<float*>(g.out) + (long long)m * g.ldo + n) = v;
           } else {

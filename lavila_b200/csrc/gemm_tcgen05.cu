@@ -265,6 +265,8 @@ extern "C" int lv_gemm_bf16(const void* A, int64_t lda, int a_mn, const void* B,
   if (k_splits > g.num_kb) k_splits = g.num_kb;
   g.kb_per_split = (g.num_kb + k_splits - 1) / k_splits;
   g.k_splits = (g.num_kb + g.kb_per_split - 1) / g.kb_per_split;
+  g.sk_total_kb = 0;
+  g.sk_kb_per_cta = 0;
   g.flags = flags | ((flags & LV_EPI_ATOMIC) ? LV_EPI_OUT_F32 : 0);
   g.out = epi->out; g.ldo = epi->ldo;
   g.out2 = epi->out2; g.ldo2 = epi->ldo2;

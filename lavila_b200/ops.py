@@ -84,11 +84,24 @@ USE_2CTA_GEMM = True    # 256x256 CTA-pair tiles (lv_gemm_bf16_2cta) whenever M 
 
 
 def wgrad_splits(m_out, n_in, k_tokens, sms=148):
+    """Split count of a weight-gradient GEMM (dW[out,in] = dY^T X, K = tokens).  Items (tile, split) are spread round-robin
+    over the CTA pairs, all equally long, so the makespan is ceil(items / pairs) item times: pick the split count in
+    [2 waves, 4.5 waves] whose items fill whole waves best (11 splits of the 27-tile qkv gradient = 297 items on 74 pairs ran
+    5 waves for 4.01 waves of work; 8 splits = 216 items = 2.92 waves run 3).  Items of one split are consecutive, so the
+    pairs of a wave share operand panels in L2."""
     bm = 256 if USE_2CTA_GEMM and m_out >= 256 else 128
-    sms = sms // 2 if bm == 256 else sms
+    units = sms // 2 if bm == 256 else sms
     tiles = ((m_out + bm - 1) // bm) * ((n_in + 255) // 256)
     kb = (k_tokens + 63) // 64
-    return max(1, min(kb, (4 * sms + tiles - 1) // tiles))
+    lo = max(1, (2 * units) // tiles)
+    hi = max(lo, min(kb, (9 * units) // (2 * tiles)))
+    best, best_eff = lo, -1.0
+    for s in range(lo, hi + 1):
+        items = tiles * s
+        eff = items / (units * ((items + units - 1) // units))
+        if eff > best_eff + 1e-9:
+            best, best_eff = s, eff
+    return max(1, min(kb, best))
 
 
 def layernorm_fwd(x, gamma, beta, eps, rows, D, *, ldx=None, y_bf16=None, y_f32=None):
