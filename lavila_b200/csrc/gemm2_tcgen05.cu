@@ -17,6 +17,8 @@
 
 #include "../../include/lavila_b200.h"
 #include "gemm_epilogue.cuh"
+#include "gemm_epilogue_rows.cuh"
+#include <cstdlib>
 #include "host_common.h"
 #include "ptx.cuh"
 
@@ -30,19 +32,28 @@ using gemm::EPI_PITCH;
 constexpr int BM_CTA = 128;   // rows per CTA; the pair covers 256
 constexpr int BN_CTA = 128;   // B rows (N) loaded per CTA
 constexpr int BK = 64;
-constexpr int STAGES = 6;
 constexpr int UMMA_K = 16;
 constexpr int A_STAGE_BYTES = BM_CTA * BK * 2;   // 16 KB
 constexpr int B_STAGE_BYTES = BN_CTA * BK * 2;   // 16 KB
 constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
 constexpr int ATOM_BYTES = 64 * BK * 2;
 constexpr int EPI_WARPS = 8;
-constexpr int EPI_BYTES = EPI_WARPS * 32 * EPI_PITCH * 4;
-constexpr int NUM_BARS = 2 * STAGES + 4;
-constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + EPI_BYTES + NUM_BARS * 8 + 16;
-static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS;
 constexpr int TMEM_COLS = 512;
+// Epilogue modes (compile time):
+//   0  transposing epilogue of gemm_epilogue.cuh (per-thread global loads / stores; every flag set), 6 operand stages
+//   1  row-per-thread epilogue with TMA stores (gemm_epilogue_rows.cuh), output-only flag sets, 5 stages + 32 KB staging
+//   2  the same + TMA prefetch of the saved pre-activation slab (dQuickGELU), 4 stages + 32 KB staging + 64 KB slabs
+__host__ __device__ constexpr int stages_of(int mode) { return mode == 0 ? 6 : (mode == 1 ? 5 : 4); }
+__host__ __device__ constexpr int epi_bytes_of(int mode) {
+  return mode == 0 ? EPI_WARPS * 32 * EPI_PITCH * 4
+                   : EPI_WARPS * (gemm::ROWS_STAGE_BYTES + (mode == 2 ? gemm::ROWS_AUX_BYTES : 0));
+}
+__host__ __device__ constexpr int num_bars_of(int mode) { return 2 * stages_of(mode) + 4 + (mode == 2 ? EPI_WARPS : 0); }
+__host__ __device__ constexpr int smem_bytes_of(int mode) {
+  return 1024 + stages_of(mode) * STAGE_BYTES + epi_bytes_of(mode) + num_bars_of(mode) * 8 + 16;
+}
+static_assert(smem_bytes_of(0) <= 227 * 1024 && smem_bytes_of(1) <= 227 * 1024 && smem_bytes_of(2) <= 227 * 1024, "shared memory budget");
 constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -93,19 +104,26 @@ __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) 
       : "memory");
 }
 
-template <int A_MN, int B_MN, int CT_FLAGS>
+template <int A_MN, int B_MN, int CT_FLAGS, int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
-gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Args g) {
+gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmO2,
+                  const __grid_constant__ CUtensorMap tmAux, const Args g) {
+  constexpr int STAGES = stages_of(MODE);
+  constexpr int EPI_BYTES = epi_bytes_of(MODE);
+  constexpr int NUM_BARS = num_bars_of(MODE);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * A_STAGE_BYTES;
-  float* sEpi = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);
+  uint8_t* sEpiRaw = smem + STAGES * STAGE_BYTES;            // 1024-byte aligned (stage sizes are multiples of 1024)
+  float* sEpi = reinterpret_cast<float*>(sEpiRaw);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + EPI_BYTES);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + STAGES;
   uint64_t* tfull_bar = bars + 2 * STAGES;
   uint64_t* tempty_bar = bars + 2 * STAGES + 2;
+  uint64_t* aux_bar = bars + 2 * STAGES + 4;                 // [EPI_WARPS], MODE 2 only
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + NUM_BARS);
 
   const int warp = threadIdx.x >> 5;
@@ -116,6 +134,14 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
+    if (MODE >= 1) {
+      prefetch_tmap(&tmO);
+      if (CT_FLAGS & LV_EPI_QUICKGELU) prefetch_tmap(&tmO2);
+    }
+    if (MODE == 2) {
+      prefetch_tmap(&tmAux);
+      for (int w = 0; w < EPI_WARPS; ++w) mbar_init(&aux_bar[w], 1);
+    }
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -209,25 +235,60 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int q = warp & 3;
     const int e = warp - 2;
     const int half = e >> 2;
-    float* buf = sEpi + e * 32 * EPI_PITCH;
     const int flags = CT_FLAGS >= 0 ? CT_FLAGS : g.flags;
-    float scale = 1.0f;
-    if (flags & LV_EPI_SCALE) {
-      scale = __ldg(g.scale_ptr);
-      if (flags & LV_EPI_SCALE_TANH) scale = tanhf(scale);
-    }
     gemm::ItemIter iter(g, cluster_id, num_clusters);
     int tile, kb0, kb1;
-    for (int it = 0; iter.next(tile, kb0, kb1); ++it) {
-      const int m_blk = tile / g.num_n_blks;
-      const int n_blk = tile - m_blk * g.num_n_blks;
-      const int as = it & 1;
-      const uint32_t aphase = (it >> 1) & 1;
-      gemm::epilogue_tile<CT_FLAGS>(g, flags, scale, buf, &tfull_bar[as], aphase, tmem_base + as * BN,
-                                    m_blk * 256 + (int)rank * BM_CTA + q * 32, n_blk * BN, half, q, lane);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_remote(&tempty_bar[as], 0);   // the leader's MMA warp owns the accumulator hand-off
+    if constexpr (MODE == 0) {
+      float* buf = sEpi + e * 32 * EPI_PITCH;
+      float scale = 1.0f;
+      if (flags & LV_EPI_SCALE) {
+        scale = __ldg(g.scale_ptr);
+        if (flags & LV_EPI_SCALE_TANH) scale = tanhf(scale);
+      }
+      for (int it = 0; iter.next(tile, kb0, kb1); ++it) {
+        const int m_blk = tile / g.num_n_blks;
+        const int n_blk = tile - m_blk * g.num_n_blks;
+        const int as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        gemm::epilogue_tile<CT_FLAGS>(g, flags, scale, buf, &tfull_bar[as], aphase, tmem_base + as * BN,
+                                      m_blk * 256 + (int)rank * BM_CTA + q * 32, n_blk * BN, half, q, lane);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_remote(&tempty_bar[as], 0);   // the leader's MMA warp owns the accumulator hand-off
+      }
+    } else {
+      uint8_t* stage = sEpiRaw + e * gemm::ROWS_STAGE_BYTES;
+      uint8_t* aux = sEpiRaw + EPI_WARPS * gemm::ROWS_STAGE_BYTES + e * gemm::ROWS_AUX_BYTES;
+      // the pre-activation slab of a tile: 4 boxes of [32 rows x 32 columns] bf16 for this warp's rows / column half
+      auto request_aux = [&](int t) {
+        const int m_blk = t / g.num_n_blks;
+        const int n_blk = t - m_blk * g.num_n_blks;
+        const int m_base = m_blk * 256 + (int)rank * BM_CTA + q * 32;
+        const int nb = n_blk * BN + half * 128;
+        int boxes = 0;
+        for (int cc = 0; cc < 4; ++cc) boxes += (nb + cc * 32 < g.N) ? 1 : 0;
+        if (boxes == 0) { mbar_arrive(&aux_bar[e]); return; }
+        mbar_arrive_expect_tx(&aux_bar[e], boxes * 2048);
+        for (int cc = 0; cc < boxes; ++cc) tma_load_2d(aux + cc * 2048, &tmAux, &aux_bar[e], nb + cc * 32, m_base);
+      };
+      bool have = iter.next(tile, kb0, kb1);
+      if (MODE == 2 && have && lane == 0) request_aux(tile);
+      for (int it = 0; have; ++it) {
+        const int m_blk = tile / g.num_n_blks;
+        const int n_blk = tile - m_blk * g.num_n_blks;
+        const int as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        uint64_t* tempty = &tempty_bar[as];
+        gemm::epilogue_rows_tile<CT_FLAGS>(g, stage, aux, &aux_bar[e], (uint32_t)(it & 1), &tmO, &tmO2, &tfull_bar[as], aphase,
+                                           tmem_base + as * BN, m_blk * 256 + (int)rank * BM_CTA + q * 32, n_blk * BN, half, q,
+                                           lane, [&]() { if (lane == 0) mbar_arrive_remote(tempty, 0); });
+        have = iter.next(tile, kb0, kb1);
+        if (MODE == 2) {
+          __syncwarp();                                       // every lane has finished reading this tile's slab
+          if (have && lane == 0) request_aux(tile);
+        }
+      }
+      if (lane == 0) tma_store_wait_all();                    // the staging tiles must outlive the stores that read them
     }
   }
 
@@ -239,35 +300,48 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   }
 }
 
-template <int A_MN, int B_MN, int CT_FLAGS>
-static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const Args& g, cudaStream_t stream) {
+struct Maps {
+  CUtensorMap A, B, O, O2, Aux;
+};
+
+template <int A_MN, int B_MN, int CT_FLAGS, int MODE>
+static int launch(const Maps& tm, const Args& g, cudaStream_t stream) {
+  constexpr int SMEM = smem_bytes_of(MODE);
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, []() {
-    attr_err = cudaFuncSetAttribute(gemm2_bf16_kernel<A_MN, B_MN, CT_FLAGS>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    attr_err = cudaFuncSetAttribute(gemm2_bf16_kernel<A_MN, B_MN, CT_FLAGS, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
   });
   if (attr_err != cudaSuccess) return set_error((int)attr_err, "gemm2: cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err));
   const int total = g.num_m_blks * g.num_n_blks * g.k_splits;
   int clusters = sm_count() / 2;
   if (g.sk_kb_per_cta > 0) clusters = (int)((g.sk_total_kb + g.sk_kb_per_cta - 1) / g.sk_kb_per_cta);
   else if (total < clusters) clusters = total;
-  gemm2_bf16_kernel<A_MN, B_MN, CT_FLAGS><<<2 * clusters, NUM_THREADS, SMEM_BYTES, stream>>>(tmA, tmB, g);
+  gemm2_bf16_kernel<A_MN, B_MN, CT_FLAGS, MODE><<<2 * clusters, NUM_THREADS, SMEM, stream>>>(tm.A, tm.B, tm.O, tm.O2, tm.Aux, g);
   return check_launch("lv_gemm_bf16 (2-CTA)");
 }
 
+// rows_mode: 0 = transposing epilogue; 1 / 2 = row-per-thread TMA-store epilogue available for this call (maps built)
 template <int A_MN, int B_MN, int F>
-static int try_spec(bool& hit, const CUtensorMap& tmA, const CUtensorMap& tmB, const Args& g, cudaStream_t st) {
+static int try_spec(bool& hit, const Maps& tm, const Args& g, int rows_mode, cudaStream_t st) {
   if constexpr (gemm::is_specialised(A_MN, B_MN, F)) {
-    if (!hit && g.flags == F) { hit = true; return launch<A_MN, B_MN, F>(tmA, tmB, g, st); }
+    if (!hit && g.flags == F) {
+      hit = true;
+      if constexpr (gemm::rows_supported(F) && !A_MN) {
+        constexpr int MODE = gemm::rows_needs_aux(F) ? 2 : 1;
+        if (rows_mode == MODE) return launch<A_MN, B_MN, F, MODE>(tm, g, st);
+      }
+      return launch<A_MN, B_MN, F, 0>(tm, g, st);
+    }
   }
   return 0;
 }
 
 template <int A_MN, int B_MN>
-static int dispatch(const CUtensorMap& tmA, const CUtensorMap& tmB, const Args& g, cudaStream_t st) {
+static int dispatch(const Maps& tm, const Args& g, int rows_mode, cudaStream_t st) {
   bool hit = false;
   int rc = 0;
-#define LV_TRY(F) if (!hit) rc = try_spec<A_MN, B_MN, (F)>(hit, tmA, tmB, g, st);
+#define LV_TRY(F) if (!hit) rc = try_spec<A_MN, B_MN, (F)>(hit, tm, g, rows_mode, st);
   LV_TRY(0)
   LV_TRY(LV_EPI_BIAS)
   LV_TRY(LV_EPI_BIAS | LV_EPI_QUICKGELU)
@@ -278,7 +352,13 @@ static int dispatch(const CUtensorMap& tmA, const CUtensorMap& tmB, const Args& 
   LV_TRY(LV_EPI_ATOMIC | LV_EPI_OUT_F32)
 #undef LV_TRY
   if (hit) return rc;
-  return launch<A_MN, B_MN, -1>(tmA, tmB, g, st);
+  return launch<A_MN, B_MN, -1, 0>(tm, g, st);
+}
+
+// LAVILA_B200_GEMM_ROWS_EPI=0 keeps the transposing epilogue everywhere (A/B runs)
+static bool rows_epilogue_enabled() {
+  static const bool on = []() { const char* e = std::getenv("LAVILA_B200_GEMM_ROWS_EPI"); return !(e && e[0] == '0'); }();
+  return on;
 }
 
 }  // namespace gemm2
@@ -301,14 +381,25 @@ extern "C" int lv_gemm_bf16_2cta(const void* A, int64_t lda, int a_mn, const voi
   if (k_splits < 1) k_splits = 1;
   LV_REQUIRE(k_splits == 1 || (flags & LV_EPI_ATOMIC), "lv_gemm_bf16_2cta: k_splits > 1 requires LV_EPI_ATOMIC");
 
-  CUtensorMap tmA, tmB;
+  Maps tm{};
   int rc;
-  if (a_mn) rc = make_tmap_2d_bf16(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 64, BK);
-  else      rc = make_tmap_2d_bf16(&tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, BK, BM_CTA);
+  if (a_mn) rc = make_tmap_2d_bf16(&tm.A, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 64, BK);
+  else      rc = make_tmap_2d_bf16(&tm.A, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, BK, BM_CTA);
   if (rc) return rc;
-  if (b_mn) rc = make_tmap_2d_bf16(&tmB, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 64, BK);
-  else      rc = make_tmap_2d_bf16(&tmB, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, BK, BN_CTA);
+  if (b_mn) rc = make_tmap_2d_bf16(&tm.B, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 64, BK);
+  else      rc = make_tmap_2d_bf16(&tm.B, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, BK, BN_CTA);
   if (rc) return rc;
+  // Row-per-thread TMA-store epilogue: output-only flag sets (and dQuickGELU) with bf16 outputs whose base / pitch TMA accepts
+  int rows_mode = 0;
+  auto tma_ok = [](const void* p, long long ld_elems) { return p && (reinterpret_cast<uintptr_t>(p) & 15) == 0 && (ld_elems & 7) == 0; };
+  if (rows_epilogue_enabled() && !a_mn && gemm::rows_supported(flags) && tma_ok(epi->out, epi->ldo) &&
+      (!(flags & LV_EPI_QUICKGELU) || tma_ok(epi->out2, epi->ldo2)) && (!(flags & LV_EPI_DQUICKGELU) || tma_ok(epi->aux, epi->ldaux))) {
+    rows_mode = gemm::rows_needs_aux(flags) ? 2 : 1;
+    rc = make_tmap_2d(&tm.O, epi->out, 2, (uint64_t)N, (uint64_t)M, (uint64_t)epi->ldo, 32, 32, 64);
+    if (!rc && (flags & LV_EPI_QUICKGELU)) rc = make_tmap_2d(&tm.O2, epi->out2, 2, (uint64_t)N, (uint64_t)M, (uint64_t)epi->ldo2, 32, 32, 64);
+    if (!rc && (flags & LV_EPI_DQUICKGELU)) rc = make_tmap_2d(&tm.Aux, epi->aux, 2, (uint64_t)N, (uint64_t)M, (uint64_t)epi->ldaux, 32, 32, 64);
+    if (rc) return rc;
+  }
 
   gemm::Args g;
   g.M = (int)M; g.N = (int)N; g.K = (int)K;
@@ -333,8 +424,8 @@ extern "C" int lv_gemm_bf16_2cta(const void* A, int64_t lda, int a_mn, const voi
   g.scale_ptr = epi->scale_ptr;
 
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (!a_mn && !b_mn) return dispatch<0, 0>(tmA, tmB, g, st);
-  if (!a_mn && b_mn) return dispatch<0, 1>(tmA, tmB, g, st);
-  if (a_mn && b_mn) return dispatch<1, 1>(tmA, tmB, g, st);
-  return dispatch<1, 0>(tmA, tmB, g, st);
+  if (!a_mn && !b_mn) return dispatch<0, 0>(tm, g, rows_mode, st);
+  if (!a_mn && b_mn) return dispatch<0, 1>(tm, g, rows_mode, st);
+  if (a_mn && b_mn) return dispatch<1, 1>(tm, g, rows_mode, st);
+  return dispatch<1, 0>(tm, g, rows_mode, st);
 }

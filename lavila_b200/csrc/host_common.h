@@ -20,6 +20,10 @@ int sm_count();                       // SMs of the current device (cached per d
 int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t inner, uint64_t rows, uint64_t ld,
                       uint32_t box_inner, uint32_t box_rows);
 
+// general form: elem_bytes 2 (bf16) or 4 (fp32); swizzle_bytes 128 or 64 (box_inner * elem_bytes must fit the swizzle span)
+int make_tmap_2d(CUtensorMap* out, const void* base, int elem_bytes, uint64_t inner, uint64_t rows, uint64_t ld,
+                 uint32_t box_inner, uint32_t box_rows, int swizzle_bytes);
+
 // small-group time attention (attention_time.cu), dispatched from lv_group_attn_fwd / lv_group_attn_bwd (mode 1, T <= 16)
 int time_attn_small_fwd(const void* qkv, long long ld_qkv, void* out, long long ld_out, float* lse, int B, int H, int T, int n,
                         cudaStream_t st);

@@ -59,24 +59,34 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
-int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t inner, uint64_t rows, uint64_t ld,
-                      uint32_t box_inner, uint32_t box_rows) {
+int make_tmap_2d(CUtensorMap* out, const void* base, int elem_bytes, uint64_t inner, uint64_t rows, uint64_t ld,
+                 uint32_t box_inner, uint32_t box_rows, int swizzle_bytes) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return set_error(-2, "cuTensorMapEncodeTiled not available (no CUDA driver?)");
-  if ((reinterpret_cast<uintptr_t>(base) & 15) || ((ld * 2) & 15))
+  if (elem_bytes != 2 && elem_bytes != 4) return set_error(-1, "make_tmap_2d: element size %d unsupported", elem_bytes);
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || ((ld * elem_bytes) & 15))
     return set_error(-1, "TMA operand must be 16-byte aligned with a 16-byte-multiple row pitch (ld=%llu)",
                      (unsigned long long)ld);
+  if (swizzle_bytes != 128 && swizzle_bytes != 64) return set_error(-1, "make_tmap_2d: swizzle %d unsupported", swizzle_bytes);
+  if ((uint64_t)box_inner * elem_bytes > (uint64_t)swizzle_bytes)
+    return set_error(-1, "make_tmap_2d: box of %u x %d bytes exceeds the %d-byte swizzle span", box_inner, elem_bytes, swizzle_bytes);
   cuuint64_t dims[2] = {inner, rows};
-  cuuint64_t strides[1] = {ld * 2};
+  cuuint64_t strides[1] = {ld * (uint64_t)elem_bytes};
   cuuint32_t box[2] = {box_inner, box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = enc(out, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                   const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     return set_error(-3, "cuTensorMapEncodeTiled failed (%d) inner=%llu rows=%llu ld=%llu box=%ux%u", (int)r,
                      (unsigned long long)inner, (unsigned long long)rows, (unsigned long long)ld, box_inner, box_rows);
   return 0;
+}
+
+int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t inner, uint64_t rows, uint64_t ld,
+                      uint32_t box_inner, uint32_t box_rows) {
+  return make_tmap_2d(out, base, 2, inner, rows, ld, box_inner, box_rows, 128);
 }
 
 }  // namespace lv
