@@ -582,17 +582,26 @@ extern "C" int lv_ssl_clip_loss_bwd(const float* img, const float* txt, const fl
 }
 
 static int gather_max_rows(int E) {
-  // co-residency of the cooperative launch and the [2E + Ng] fp32 row buffer (<= 48 KB) both bound Ng = W * Bl
-  long long by_smem = (48 * 1024) / (long long)sizeof(float) - 2ll * E;
-  if (by_smem <= 0) return 0;
-  int per_sm = 0;
-  const size_t smem = (size_t)48 * 1024;     // worst case: occupancy only drops with more shared memory
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, loss::clip_loss_fwd_gather_kernel, loss::THREADS, smem) != cudaSuccess) {
+  // Two bounds on Ng = W * Bl: the [2E + Ng] fp32 row buffer (dynamic) plus the kernel's static shared memory must fit the
+  // 48 KB default limit, and all Ng CTAs of the cooperative launch must be co-resident (occupancy falls as the buffer grows).
+  cudaFuncAttributes fa;
+  if (cudaFuncGetAttributes(&fa, loss::clip_loss_fwd_gather_kernel) != cudaSuccess) {
     cudaGetLastError();
     return 0;
   }
-  const long long by_occ = (long long)per_sm * sm_count();
-  return (int)(by_occ < by_smem ? by_occ : by_smem);
+  const long long by_smem = ((long long)48 * 1024 - (long long)fa.sharedSizeBytes) / (long long)sizeof(float) - 2ll * E;
+  if (by_smem <= 0) return 0;
+  const int sms = sm_count();
+  for (long long ng = by_smem; ng >= 1; ng -= (ng > 64 ? 32 : 1)) {
+    int per_sm = 0;
+    const size_t smem = (size_t)(2 * E + ng) * sizeof(float);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, loss::clip_loss_fwd_gather_kernel, loss::THREADS, smem) != cudaSuccess) {
+      cudaGetLastError();
+      return 0;
+    }
+    if ((long long)per_sm * sms >= ng) return (int)ng;
+  }
+  return 0;
 }
 
 extern "C" int lv_clip_loss_gather_max_rows(int E) {

@@ -59,7 +59,8 @@ def _peer_exchange(state, B, E, dev, world_size):
             why = "global batch %d > %d rows supported by the cooperative kernel" % (B * world_size, max_rows)
         else:
             try:
-                import torch.distributed._symmetric_memory  # noqa: F401
+                import importlib
+                importlib.import_module("torch.distributed._symmetric_memory")
                 from .distributed_utils import PeerEmbeddingExchange
             except Exception as e:
                 why = "torch symmetric memory unavailable (%r)" % (e,)
