@@ -565,6 +565,15 @@ int fill(battn::Params& p, int mode, int B, int H, int T, int n) {
 
 int big_group_attn_fwd(const void* qkv, long long ld_qkv, void* out, long long ld_out, float* lse, int mode, int B, int H, int T,
                        int n, cudaStream_t st) {
+  if (mode == 0 && flash_tc_enabled() && (ld_qkv % 8) == 0 && (ld_out % 8) == 0 && ((uintptr_t)qkv & 15) == 0) {
+    // space attention of TimeSformer-L/14 (257 / 577 keys per group): tcgen05 key-tiled kernel, the CLS key / value row of the
+    // clip appended to the group's last key tile
+    const int D = H * 64;
+    const long long N = 1 + (long long)T * n;
+    const __nv_bfloat16* base = (const __nv_bfloat16*)qkv;
+    return flash_attn_fwd_tc(base, ld_qkv, N, D, base + D, base + 2 * D, ld_qkv, N, D, 64, out, ld_out, lse, B, T, H, n, n, 1, n, 1, n,
+                             1, 0, 0.125f, st);
+  }
   battn::Params p{};
   int rc = fill(p, mode, B, H, T, n);
   if (rc) return rc;

@@ -195,6 +195,13 @@ static int flash_launch(const void* q, int64_t ld_q, int64_t q_rows, const void*
   LV_REQUIRE(q && k && v && out && B > 0 && H > 0 && Lq > 0 && (Lk > 0 || lk_dev), "%s: bad arguments", what);
   LV_REQUIRE(ld_q % 8 == 0 && ld_kv % 8 == 0 && ld_out % 8 == 0 && kv_head_stride % 8 == 0, "%s: strides must be multiples of 8 elements", what);
   LV_REQUIRE(((uintptr_t)q & 15) == 0 && ((uintptr_t)k & 15) == 0 && ((uintptr_t)v & 15) == 0 && ((uintptr_t)out & 15) == 0, "%s: pointers must be 16-byte aligned", what);
+  // >= 64 query rows per (batch, head) -- CoCa pooling (256 x 1025), teacher-forced cross-attention (77 x 256) -- run the tcgen05
+  // key-tiled kernel (flash_tc.cu); causal self-attention from 128 rows (at 77 x 77 the 128-row tile is mostly masked: measured
+  // 0.27 ms vs 0.16 ms here).  Decoding steps (1 query row per sequence: a matrix-vector product per head, HBM-bound) and the
+  // device-resident key count of the CUDA-graph replay stay on the mma.sync kernel below.
+  if ((Lq >= 128 || (Lq >= 64 && !causal)) && !lk_dev && flash_tc_enabled())
+    return flash_attn_fwd_tc(q, ld_q, q_rows, H * flash::HD, k, v, ld_kv, kv_rows, (H - 1) * kv_head_stride + flash::HD, kv_head_stride,
+                             out, ld_out, nullptr, B, 1, H, Lq, Lk, 0, 0, 0, 0, 0, causal, scale, (cudaStream_t)stream);
   flash::Params p{};
   p.q = (const __nv_bfloat16*)q; p.k = (const __nv_bfloat16*)k; p.v = (const __nv_bfloat16*)v; p.out = (__nv_bfloat16*)out;
   p.ld_q = ld_q; p.ld_kv = ld_kv; p.ld_out = ld_out; p.q_rows = q_rows; p.kv_rows = kv_rows;

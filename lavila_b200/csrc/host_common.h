@@ -38,6 +38,15 @@ int big_group_attn_bwd(const void* qkv, long long ld_qkv, const void* out, long 
                        long long ld_dout, void* dqkv, long long ld_dqkv, float* dcls_kv, int mode, int B, int H, int T, int n,
                        cudaStream_t st);
 
+// key-tiled attention forward on tcgen05 (flash_tc.cu): q / k / v point at head 0 of batch element 0; group g of batch b owns
+// query rows b*q_rows + q_grp_row0 + g*q_grp_stride .. +Lq and key rows b*kv_rows + kv_grp_row0 + g*kv_grp_stride .. +Lk
+// (+ the extra key / value row b*kv_rows when has_extra); lse (optional) is [row][H].
+int flash_attn_fwd_tc(const void* q, long long ld_q, long long q_rows, int q_cols, const void* k, const void* v, long long ld_kv,
+                      long long kv_rows, int kv_cols, int kv_head_stride, void* out, long long ld_out, float* lse, int B, int G,
+                      int H, int Lq, int Lk, long long q_grp_row0, long long q_grp_stride, long long kv_grp_row0,
+                      long long kv_grp_stride, int has_extra, int causal, float scale, cudaStream_t st);
+bool flash_tc_enabled();   // LAVILA_B200_FLASH_TC=0 keeps the mma.sync kernels (A/B runs)
+
 }  // namespace lv
 
 #define LV_REQUIRE(cond, ...)                                  \

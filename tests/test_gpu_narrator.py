@@ -114,7 +114,11 @@ def test_kv_cached_decoding_equals_full_prefix():
 
 @pytest.mark.parametrize("B,H,Lq,Lk,mqa,causal", [(2, 3, 5, 40, False, False), (2, 25, 77, 256, False, False),
                                                    (3, 4, 77, 77, False, True), (2, 12, 256, 785, True, False),
-                                                   (1, 2, 1, 1, False, True), (2, 2, 130, 130, False, True)])
+                                                   (1, 2, 1, 1, False, True), (2, 2, 130, 130, False, True),
+                                                   # >= 64 query rows: the tcgen05 key-tiled kernel (flash_tc.cu)
+                                                   (2, 3, 64, 64, False, True), (2, 5, 200, 300, False, False),
+                                                   (1, 25, 128, 1025, True, False), (3, 25, 77, 256, False, False),
+                                                   (2, 4, 129, 257, False, True), (1, 2, 300, 16, False, False)])
 def test_flash_attention(B, H, Lq, Lk, mqa, causal):
     from lavila_b200 import ops
     torch.manual_seed(1)
