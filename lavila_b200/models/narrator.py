@@ -3,7 +3,8 @@
 generate() keeps the reference's sampling algorithm (temperature / top-k / top-p warpers from `transformers`,
 torch.multinomial, entropy-based "ppl") but (a) projects the cross-attention K/V of the 256 video tokens once per clip
 instead of once per decoding step and layer, and (b) evaluates the LM head on the last position only -- both leave
-every returned value unchanged (SURVEY.md 8(a) a16/a19 note the waste).  beam_sample / group_beam_search are "next"."""
+every returned value unchanged (SURVEY.md 8(a) a16/a19 note the waste).  beam_sample / group_beam_search (narrator.py:149-366)
+run the reference's candidate selection on the same decoder with the scorer of beam_search.py."""
 import torch
 import torch.nn.functional as F
 from torch import nn
@@ -124,6 +125,108 @@ class VCLM_HF(nn.Module):
                     condition_text_ids = torch.cat((generated_text_ids, next_token), dim=1)
                 generated_text_ids = torch.cat((generated_text_ids, next_token), dim=1)
         return generated_text_ids, torch.exp(nlls / num_tokens)
+
+
+    # ------------------------------------------------------------------------------------------------ beam decoding
+    def _last_logprobs(self, ids, ctx, kv_cache):
+        """log-softmax of the next-token logits of every row (the decoder re-reads the prefix; the clip's cross-attention
+        K / V are projected once -- beams of a batch element are only permuted among themselves, so the cache stays valid)."""
+        out = self.text_decoder(ids.contiguous(), encoder_hidden_states=ctx, last_only=True, ctx_kv_cache=kv_cache)
+        return F.log_softmax(out.logits[:, -1, :], dim=-1)
+
+    @torch.no_grad()
+    def beam_sample(self, image_tokens, tokenizer, target=None, max_text_length=77, top_k=None, top_p=None, temperature=1.0,
+                    length_penalty=1., num_beams=3, num_return_sequences=1, teacher_forcing=False, early_stopping=False):
+        """narrator.py:149-241: stochastic beam search -- per step, 2 x num_beams continuations are SAMPLED (torch.multinomial)
+        from the warped joint distribution over (beam, token), sorted by score and handed to the scorer."""
+        from .beam_search import BeamSearchScorer
+        device = image_tokens.device
+        n_clips = image_tokens.shape[0]
+        per_clip = num_beams * num_return_sequences
+        ids = torch.full((n_clips * per_clip, 1), tokenizer.bos_token_id, device=device, dtype=torch.long)
+        ctx = image_tokens.repeat_interleave(per_clip, dim=0)
+        warper = self._get_logits_warper(top_k=top_k, top_p=top_p, typical_p=None, temperature=temperature, num_beams=num_beams)
+        scorer = BeamSearchScorer(batch_size=n_clips * num_return_sequences, num_beams=num_beams, device=device,
+                                  length_penalty=length_penalty)
+        rows = n_clips * num_return_sequences                 # independent beam searches (one per returned sequence)
+        beam_scores = torch.zeros(rows * num_beams, device=device)
+        reached_eos = torch.zeros(ids.shape[0], dtype=torch.bool, device=device)
+        kv_cache = {}
+        cand_tokens = cand_beams = None
+        for _ in range(max_text_length - 1):
+            logp = self._last_logprobs(ids, ctx, kv_cache)                         # [rows * num_beams, V]
+            joint = warper(ids, logp + beam_scores[:, None].expand_as(logp))       # the reference warps the JOINT scores (:199)
+            V = joint.shape[-1]
+            joint = joint.view(rows, num_beams * V)
+            picks = torch.multinomial(F.softmax(joint, dim=-1), num_samples=2 * num_beams)
+            cand_scores = torch.gather(joint, -1, picks)
+            cand_scores, order = torch.sort(cand_scores, descending=True, dim=1)
+            picks = torch.gather(picks, -1, order)
+            cand_beams = torch.div(picks, V, rounding_mode="floor")
+            cand_tokens = picks % V
+            step = scorer.process(ids, cand_scores, cand_tokens, cand_beams, pad_token_id=tokenizer.pad_token_id,
+                                  eos_token_id=tokenizer.eos_token_id)
+            beam_scores = step["next_beam_scores"]
+            ids = torch.cat([ids[step["next_beam_indices"], :], step["next_beam_tokens"].unsqueeze(-1)], dim=-1)
+            reached_eos = reached_eos | (ids[:, -1] == tokenizer.eos_token_id)
+            if scorer.is_done or bool(torch.all(reached_eos)):
+                break
+        fin = scorer.finalize(ids, beam_scores, cand_tokens, cand_beams, pad_token_id=tokenizer.pad_token_id,
+                              eos_token_id=tokenizer.eos_token_id, max_length=max_text_length)
+        return fin["sequences"], fin["sequence_scores"]
+
+    @torch.no_grad()
+    def group_beam_search(self, image_tokens, tokenizer, target=None, max_text_length=77, top_k=None, top_p=None,
+                          temperature=1.0, length_penalty=1., num_beams=6, num_beam_groups=3, num_return_sequences=1,
+                          teacher_forcing=False, early_stopping=False):
+        """narrator.py:243-366: the beams of a clip are split into num_beam_groups groups that are advanced one after the other
+        on the SAME decoder output of the step, each taking its top 2 x group_size continuations (the reference applies no
+        diversity penalty between groups -- its logits_processor call is commented out, :309-310 -- and neither does this)."""
+        from .beam_search import BeamSearchScorer
+        device = image_tokens.device
+        n_clips = image_tokens.shape[0]
+        ids = torch.full((n_clips * num_beams, 1), tokenizer.bos_token_id, device=device, dtype=torch.long)
+        ctx = image_tokens.repeat_interleave(num_beams, dim=0)
+        warper = self._get_logits_warper(top_k=top_k, top_p=top_p, typical_p=None, temperature=temperature, num_beams=num_beams)
+        scorer = BeamSearchScorer(batch_size=n_clips, num_beams=num_beams, num_beam_groups=num_beam_groups,
+                                  num_beam_hyps_to_keep=num_return_sequences, device=device, length_penalty=length_penalty)
+        gsz = num_beams // num_beam_groups
+        beam_scores = torch.full((n_clips, num_beams), -1e9, dtype=torch.float, device=device)
+        beam_scores[:, ::gsz] = 0                       # one live beam per group at the start
+        beam_scores = beam_scores.view(-1)
+        reached_eos = torch.zeros(ids.shape[0], dtype=torch.bool, device=device)
+        # rows of group g across the batch, in batch order
+        base = torch.arange(n_clips, device=device).view(-1, 1) * num_beams
+        group_rows = [(base + torch.arange(g * gsz, min((g + 1) * gsz, num_beams), device=device).view(1, -1)).reshape(-1)
+                      for g in range(num_beam_groups)]
+        kv_cache = {}
+        cand_tokens = cand_beams = None
+        for _ in range(max_text_length - 1):
+            logp_all = self._last_logprobs(ids, ctx, kv_cache)
+            new_last = torch.zeros(n_clips * num_beams, dtype=ids.dtype, device=device)
+            for rows_g in group_rows:
+                g_ids = ids[rows_g]
+                g_size = rows_g.numel() // n_clips
+                logp = logp_all[rows_g]
+                V = logp.shape[-1]
+                joint = warper(ids, logp + beam_scores[rows_g].unsqueeze(-1))
+                joint = joint.view(n_clips, g_size * V)
+                cand_scores, picks = torch.topk(joint, 2 * g_size, dim=1, largest=True, sorted=True)
+                cand_beams = torch.div(picks, V, rounding_mode="floor")
+                cand_tokens = picks % V
+                step = scorer.process(g_ids, cand_scores, cand_tokens, cand_beams, pad_token_id=tokenizer.pad_token_id,
+                                      eos_token_id=tokenizer.eos_token_id, beam_indices=None)
+                beam_scores[rows_g] = step["next_beam_scores"]
+                picked = step["next_beam_indices"]
+                ids[rows_g] = g_ids[picked]
+                new_last[rows_g] = step["next_beam_tokens"]
+            ids = torch.cat([ids, new_last.unsqueeze(-1)], dim=-1)
+            reached_eos = reached_eos | (ids[:, -1] == tokenizer.eos_token_id)
+            if scorer.is_done or bool(torch.all(reached_eos)):
+                break
+        fin = scorer.finalize(ids, beam_scores, cand_tokens, cand_beams, pad_token_id=tokenizer.pad_token_id,
+                              eos_token_id=tokenizer.eos_token_id, max_length=max_text_length, beam_indices=None)
+        return fin["sequences"], fin["sequence_scores"]
 
     def _decode_state(self, image_tokens, max_len):
         """Persistent buffers of the graph-captured decoding step, keyed by (sequences, max length, device, weight versions):

@@ -112,6 +112,31 @@ def test_kv_cached_decoding_equals_full_prefix():
     assert rel_l2(outs2[0][1], outs2[1][1]) < 1e-4
 
 
+def test_beam_decoding_on_the_kernels():
+    """beam_sample / group_beam_search (narrator.py:149-366) on the CUDA path.  Host logic is pinned exactly on CPU
+    (tests/test_host_narrator_cpu.py); here: shapes / dtypes, and the returned score of every open-ended sequence equals the
+    length-normalised sum of its token log-probabilities recomputed by teacher forcing through the same kernels."""
+    cfg, m, frames = _setup()
+    tok = m.encode_image(frames)
+    t = SimpleNamespace(bos_token_id=cfg["vocab_size"] - 1, eos_token_id=cfg["vocab_size"] - 1, pad_token_id=0)
+    L = 8
+    seq, sc = m.group_beam_search(tok, t, num_beams=4, num_beam_groups=2, num_return_sequences=1, max_text_length=L)
+    assert seq.dtype == torch.int64 and seq.shape[0] == tok.shape[0] and seq.shape[1] <= L and sc.shape == (tok.shape[0],)
+    assert bool((seq[:, 0] == t.bos_token_id).all()) and bool(torch.isfinite(sc).all())
+    checked = 0
+    for b in range(seq.shape[0]):
+        row = seq[b]
+        if row.shape[0] == L and not bool(((row[1:] == t.eos_token_id) | (row[1:] == t.pad_token_id)).any()):
+            logits = m.text_decoder(row[None, :-1].contiguous(), encoder_hidden_states=tok[b:b + 1]).logits[0]
+            lp = torch.log_softmax(logits.float(), dim=-1).gather(1, row[1:, None]).sum()
+            assert abs(float(lp) / L - float(sc[b])) < 2e-2 * max(1.0, abs(float(sc[b]))), (float(lp) / L, float(sc[b]))
+            checked += 1
+    assert checked >= 1
+    torch.manual_seed(3)
+    seq2, sc2 = m.beam_sample(tok, t, num_beams=3, num_return_sequences=2, max_text_length=7, top_p=0.95, temperature=0.7)
+    assert seq2.shape[0] == 2 * tok.shape[0] and seq2.shape[1] <= 7 and bool(torch.isfinite(sc2).all())
+
+
 @pytest.mark.parametrize("B,H,Lq,Lk,mqa,causal", [(2, 3, 5, 40, False, False), (2, 25, 77, 256, False, False),
                                                    (3, 4, 77, 77, False, True), (2, 12, 256, 785, True, False),
                                                    (1, 2, 1, 1, False, True), (2, 2, 130, 130, False, True),

@@ -91,3 +91,101 @@ def test_use_half_is_accepted(monkeypatch):
     assert m.half() is m and all(p.dtype == torch.float32 for p in m.parameters())
     tok = m.encode_image(frames.half())
     assert tok.dtype == torch.float32 and rel_l2(tok, ref) < 5e-3
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# beam_sample / group_beam_search (narrator.py:149-366): the product's candidate selection + its BeamSearchScorer
+# (lavila_b200/models/beam_search.py) on the kernel test doubles, against the reference's own decoding code run with the oracle
+# scorer (tests/golden/make_golden_beam.py).
+BEAM = torch.load(os.path.join(os.path.dirname(__file__), "golden", "narrator_beam.pt"), weights_only=False)
+
+
+def _beam_setup(monkeypatch):
+    ops_doubles.install(monkeypatch)
+    cfg = BEAM["cfg"]
+    model = _build(cfg, ON.init_narrator_params(cfg, seed=0))
+    frames, _ = synthetic_batch(dict(cfg["visual"], context_length=8, vocab_size=8), BEAM["batch"], seed=BEAM["frames_seed"])
+    tok = model.encode_image(frames)
+    assert rel_l2(tok, BEAM["image_tokens"]) < 2e-2
+    t = SimpleNamespace(bos_token_id=cfg["vocab_size"] - 1, eos_token_id=cfg["vocab_size"] - 1, pad_token_id=0)
+    return model, tok, t
+
+
+@pytest.mark.parametrize("case", [k for k, v in BEAM["cases"].items() if v["kind"] == "group"])
+def test_group_beam_search_matches_reference(case, monkeypatch):
+    """Deterministic (top-k): the ids are the reference's, the scores agree to fp32 round-off of the doubles."""
+    model, tok, t = _beam_setup(monkeypatch)
+    c = BEAM["cases"][case]
+    seq, sc = model.group_beam_search(tok, t, **c["kw"])
+    assert seq.dtype == torch.int64 and tuple(seq.shape) == tuple(c["sequences"].shape)
+    assert torch.equal(seq, c["sequences"]), (seq, c["sequences"])
+    assert torch.allclose(sc, c["scores"], atol=5e-3, rtol=1e-3)      # the doubles round GEMM operands to bf16 like the kernels
+
+
+@pytest.mark.parametrize("case", [k for k, v in BEAM["cases"].items() if v["kind"] == "sample"])
+def test_beam_sample_real_decoder_under_the_same_seed(case, monkeypatch):
+    """With the real decoder the joint scores differ from the reference's by the bf16 operand rounding the doubles model, which
+    can move an occasional multinomial draw: shapes / BOS / finiteness always, and at least half of the returned sequences
+    identical to the reference's (the exact check of the host logic is the stub-decoder test below)."""
+    model, tok, t = _beam_setup(monkeypatch)
+    c = BEAM["cases"][case]
+    torch.manual_seed(c["seed"])
+    seq, sc = model.beam_sample(tok, t, **c["kw"])
+    assert tuple(seq.shape) == tuple(c["sequences"].shape) and bool((seq[:, 0] == t.bos_token_id).all())
+    assert bool(torch.isfinite(sc).all())
+    same = (seq == c["sequences"]).all(dim=1)
+    assert int(same.sum()) * 2 >= same.numel(), (seq, c["sequences"])
+    assert torch.allclose(sc[same], c["scores"][same], atol=2e-2, rtol=1e-3)
+
+
+@pytest.mark.parametrize("case", [k for k, v in BEAM["cases"].items() if v["kind"].startswith("stub")])
+def test_beam_decoding_host_logic_is_exact_on_a_stub_decoder(case, monkeypatch):
+    """Decoder replaced by a table look-up that is an exact function of the ids (same stub as in the golden run): every id and
+    every score of beam_sample (same torch seed) and group_beam_search must equal the reference's bit for bit."""
+    from tests.golden.make_golden_beam import StubDecoder
+    model, tok, t = _beam_setup(monkeypatch)
+    model.text_decoder = StubDecoder(BEAM["cfg"]["vocab_size"])
+    c = BEAM["cases"][case]
+    if c["kind"] == "stub_sample":
+        torch.manual_seed(c["seed"])
+        seq, sc = model.beam_sample(tok, t, **c["kw"])
+    else:
+        seq, sc = model.group_beam_search(tok, t, **c["kw"])
+    assert torch.equal(seq, c["sequences"]), (seq, c["sequences"])
+    assert torch.equal(sc, c["scores"])
+
+
+def test_beam_scorer_equals_oracle_scorer_on_random_steps():
+    """The product's vectorised scorer and the oracle's loop restatement agree step by step on random candidate streams
+    (including EOS hits inside and outside the first group_size ranks, finished batch elements and the final ranking)."""
+    from lavila_b200.models.beam_search import BeamSearchScorer as P
+    from oracle.beam_scorer import BeamSearchScorer as O
+    g = torch.Generator().manual_seed(3)
+    for trial in range(6):
+        B, nb, groups, keep, V, eos = 3, 4, (1 if trial % 2 else 2), (1 if trial < 3 else 2), 11, 10
+        gs = nb // groups
+        a = P(B, nb, "cpu", length_penalty=1.0 + 0.5 * (trial % 3), num_beam_groups=groups, num_beam_hyps_to_keep=keep)
+        b = O(B, nb, "cpu", length_penalty=1.0 + 0.5 * (trial % 3), num_beam_groups=groups, num_beam_hyps_to_keep=keep)
+        ids = torch.full((B * nb, 1), eos, dtype=torch.long)
+        scores = torch.zeros(B * nb)
+        for step in range(7):
+            new_last = torch.zeros(B * nb, dtype=torch.long)
+            for grp in range(groups):
+                rows = (torch.arange(B).view(-1, 1) * nb + torch.arange(grp * gs, (grp + 1) * gs).view(1, -1)).reshape(-1)
+                cs, _ = torch.sort(torch.randn(B, 2 * gs, generator=g) - step, descending=True, dim=1)
+                ct = torch.randint(0, V, (B, 2 * gs), generator=g)
+                ci = torch.randint(0, gs, (B, 2 * gs), generator=g)
+                # keep enough non-EOS candidates for the beam to refill
+                ct[:, -gs:] = torch.randint(0, V - 1, (B, gs), generator=g)
+                ra = a.process(ids[rows], cs, ct, ci, pad_token_id=0, eos_token_id=eos)
+                rb = b.process(ids[rows], cs, ct, ci, pad_token_id=0, eos_token_id=eos)
+                for k in ("next_beam_scores", "next_beam_tokens", "next_beam_indices"):
+                    assert torch.equal(ra[k], rb[k]), (trial, step, k)
+                scores[rows] = ra["next_beam_scores"]
+                ids[rows] = ids[rows][ra["next_beam_indices"]]
+                new_last[rows] = ra["next_beam_tokens"]
+            ids = torch.cat([ids, new_last.unsqueeze(-1)], dim=-1)
+            assert bool(a.is_done) == bool(b.is_done)
+        fa = a.finalize(ids, scores, None, None, max_length=9, pad_token_id=0, eos_token_id=eos)
+        fb = b.finalize(ids, scores, None, None, max_length=9, pad_token_id=0, eos_token_id=eos)
+        assert torch.equal(fa["sequences"], fb["sequences"]) and torch.allclose(fa["sequence_scores"], fb["sequence_scores"])
