@@ -243,6 +243,14 @@ int lv_ssl_clip_loss_bwd(const float* img, const float* txt, const float* scale_
                          float scale_grad_scale, int Ng, int E, int r0, int Nl, float* d_img, float* d_txt, float* d_scales,
                          void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Sampling: temperature + nucleus (top-p) filter of next-token logits, in place (lavila/models/narrator.py:131,368-389:
+ * TemperatureLogitsWarper then TopPLogitsWarper(min_tokens_to_keep = 1) of transformers).  logits fp32 [rows][ld], V <= 56 320
+ * (a row is staged in shared memory); every entry becomes logits / temperature, or -inf if the library would remove it
+ * (ascending cumulative probability <= 1 - top_p; ties at the threshold: the same number removed, lowest indices first).
+ * ---------------------------------------------------------------------------------------------- */
+int lv_top_p_filter(float* logits, int64_t ld, int rows, int V, float temperature, float top_p, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

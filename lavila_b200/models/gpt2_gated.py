@@ -153,16 +153,25 @@ class GPT2Block(nn.Module):
             _linear(y, ca.q_attn, M, q)
             kv = ctx_kv_cache.get(self.layer_idx)
             stale = ctx_kv_cache.get("_stale")    # layers whose (persistent) K/V buffer belongs to a previous batch of clips
+            # `generate(num_return_sequences=R)` repeats every clip's video tokens R times (narrator.py:108): the R sequences of
+            # a clip share ONE set of cross-attention keys / values.  They are projected once per CLIP and the R x Lq query rows
+            # of a clip (consecutive rows of q) attend to them as one attention problem -- 1/R of the K/V traffic of a decoding
+            # step (12.6 GB -> 1.3 GB per step for GPT-2 XL at 32 clips x 10 sequences), same numbers.
+            rep = int(ctx_kv_cache.get("_repeat", 1))
+            if rep < 1 or B % rep != 0:
+                rep = 1
+            clips = B // rep
             if kv is None or (stale is not None and self.layer_idx in stale):
                 # K/V of the video tokens are projected once per clip, not once per decoding step
                 if kv is None:
-                    kv = torch.empty(B * ctx_rows, 2 * H, device=dev, dtype=BF16)
+                    kv = torch.empty(clips * ctx_rows, 2 * H, device=dev, dtype=BF16)
                     ctx_kv_cache[self.layer_idx] = kv
-                _linear(ctx_bf16, ca.c_attn, B * ctx_rows, kv)
+                src = ctx_bf16 if rep == 1 else ctx_bf16.view(clips, rep, ctx_rows, H)[:, 0].contiguous().view(clips * ctx_rows, H)
+                _linear(src, ca.c_attn, clips * ctx_rows, kv)
                 if stale is not None:
                     stale.discard(self.layer_idx)
             att = torch.empty(M, H, device=dev, dtype=BF16)
-            ops.flash_attn_fwd(q, kv, kv[:, H:], att, B, heads, Lq, ctx_rows, q_rows=Lq, kv_rows=ctx_rows, ld_q=H,
+            ops.flash_attn_fwd(q, kv, kv[:, H:], att, clips, heads, rep * Lq, ctx_rows, q_rows=rep * Lq, kv_rows=ctx_rows, ld_q=H,
                                ld_kv=2 * H, ld_out=H, causal=False)
             h2 = torch.empty(M, H, device=dev, dtype=F32)
             gate = getattr(self, "alpha_cattn", None)

@@ -5,9 +5,13 @@ torch.multinomial, entropy-based "ppl") but (a) projects the cross-attention K/V
 instead of once per decoding step and layer, and (b) evaluates the LM head on the last position only -- both leave
 every returned value unchanged (SURVEY.md 8(a) a16/a19 note the waste).  beam_sample / group_beam_search (narrator.py:149-366)
 run the reference's candidate selection on the same decoder with the scorer of beam_search.py."""
+import os
+
 import torch
 import torch.nn.functional as F
 from torch import nn
+
+from .. import ops
 
 from .coca import CrossAttention, LayerNorm
 from .timesformer import SpaceTimeTransformer
@@ -67,13 +71,16 @@ class VCLM_HF(nn.Module):
         generated_text_ids = torch.LongTensor([[tokenizer.bos_token_id]] * image_tokens.shape[0]).to(device)
         condition_text_ids = generated_text_ids.clone()
         logits_warper = self._get_logits_warper(top_k=top_k, top_p=top_p, typical_p=None, temperature=temperature, num_beams=1)
+        # the fused temperature + top-p kernel covers the script's sampling setting (main_infer_narrator.py:57-60: top_p, no top_k)
+        fused_filter = (top_p is not None and 0.0 < top_p < 1.0 and not top_k and image_tokens.is_cuda
+                        and os.environ.get("LAVILA_B200_FUSED_SAMPLING", "1") == "1")
         nlls, num_tokens = torch.zeros(image_tokens.shape[0]).to(device), torch.zeros(image_tokens.shape[0]).to(device)
         is_reach_eos = torch.zeros(image_tokens.shape[0]).bool().to(device)
         use_cache = use_kv_cache and not teacher_forcing
-        import os
         use_graph = use_cache and image_tokens.is_cuda and os.environ.get("LAVILA_B200_DECODE_GRAPH", "1") == "1"
-        st = self._decode_state(image_tokens, max_text_length) if use_graph else None
+        st = self._decode_state(image_tokens, max_text_length, num_return_sequences) if use_graph else None
         kv_cache = st["ctx"] if st is not None else {}
+        kv_cache["_repeat"] = num_return_sequences      # rows r*R .. r*R+R-1 carry the same video tokens: shared cross K/V
         self_cache = st["self"] if st is not None else ({"max_len": max_text_length} if use_cache else None)
         with torch.no_grad():
             for i in range(max_text_length - 1):
@@ -113,7 +120,14 @@ class VCLM_HF(nn.Module):
                     nll = torch.special.entr(F.softmax(next_token_logits, dim=1)).sum(dim=1)
                     nlls += nll * (~is_reach_eos)
                     num_tokens += (~is_reach_eos)
-                next_token_logits = logits_warper(generated_text_ids, next_token_logits)
+                if fused_filter:
+                    # TemperatureLogitsWarper + TopPLogitsWarper(min_tokens_to_keep=1) as ONE kernel (csrc/sampling.cu): the same
+                    # surviving token set found by a radix select instead of a [sequences x vocab] sort per step
+                    if not next_token_logits.is_contiguous() and next_token_logits.stride(-1) != 1:
+                        next_token_logits = next_token_logits.contiguous()
+                    next_token_logits = ops.top_p_filter_(next_token_logits, temperature if temperature is not None else 1.0, top_p)
+                else:
+                    next_token_logits = logits_warper(generated_text_ids, next_token_logits)
                 filtered_p = F.softmax(next_token_logits, dim=-1)
                 next_token = torch.multinomial(filtered_p, num_samples=1)
                 is_reach_eos = is_reach_eos | (next_token[:, 0] == tokenizer.eos_token_id)
@@ -151,7 +165,7 @@ class VCLM_HF(nn.Module):
         rows = n_clips * num_return_sequences                 # independent beam searches (one per returned sequence)
         beam_scores = torch.zeros(rows * num_beams, device=device)
         reached_eos = torch.zeros(ids.shape[0], dtype=torch.bool, device=device)
-        kv_cache = {}
+        kv_cache = {"_repeat": per_clip}
         cand_tokens = cand_beams = None
         for _ in range(max_text_length - 1):
             logp = self._last_logprobs(ids, ctx, kv_cache)                         # [rows * num_beams, V]
@@ -199,7 +213,7 @@ class VCLM_HF(nn.Module):
         base = torch.arange(n_clips, device=device).view(-1, 1) * num_beams
         group_rows = [(base + torch.arange(g * gsz, min((g + 1) * gsz, num_beams), device=device).view(1, -1)).reshape(-1)
                       for g in range(num_beam_groups)]
-        kv_cache = {}
+        kv_cache = {"_repeat": num_beams}
         cand_tokens = cand_beams = None
         for _ in range(max_text_length - 1):
             logp_all = self._last_logprobs(ids, ctx, kv_cache)
@@ -228,13 +242,13 @@ class VCLM_HF(nn.Module):
                               eos_token_id=tokenizer.eos_token_id, max_length=max_text_length, beam_indices=None)
         return fin["sequences"], fin["sequence_scores"]
 
-    def _decode_state(self, image_tokens, max_len):
+    def _decode_state(self, image_tokens, max_len, repeat=1):
         """Persistent buffers of the graph-captured decoding step, keyed by (sequences, max length, device, weight versions):
         per-layer self-attention KV caches, cross-attention K/V buffers (refilled in place for every new batch of clips),
         the static input ids / position scalars and the captured graph.  Weights changing (training) drop the state."""
         from ..engine import param_generation
         ver = (sum(p._version for p in self.text_decoder.parameters()), param_generation())
-        key = (image_tokens.shape[0], image_tokens.shape[1], max_len, str(image_tokens.device), ver)
+        key = (image_tokens.shape[0], image_tokens.shape[1], max_len, str(image_tokens.device), ver, int(repeat))
         store = self.__dict__.setdefault("_decode_states", {})
         st = store.get(key)
         if st is None:

@@ -309,3 +309,12 @@ def clip_loss_fwd_gather(img_local, txt_local, peers_dev_ptr, rank, W, Bl, step,
 def clip_loss_gather_max_rows(E):
     """Largest global batch W*B the fused gather + loss kernel supports on the current device (0: not supported)."""
     return int(L.lib().lv_clip_loss_gather_max_rows(int(E)))
+
+
+def top_p_filter_(logits, temperature, top_p):
+    """In place: logits <- logits / temperature, -inf where nucleus filtering (top_p, min_tokens_to_keep = 1) removes the token."""
+    _check_cuda(logits)
+    rows, V = logits.shape
+    rc = L.lib().lv_top_p_filter(logits.data_ptr(), logits.stride(0), rows, V, float(temperature), float(top_p), _stream())
+    L.check(rc, "lv_top_p_filter")
+    return logits

@@ -423,7 +423,17 @@ DOUBLES = ("gemm", "wgrad_splits", "layernorm_fwd", "layernorm_bwd", "group_attn
            "cls_attn_bwd", "cls_kv_finalize", "cls_query_attn_fwd", "cls_query_attn_bwd", "add_rows", "cast_bf16", "colsum_bf16",
            "patch_im2col", "embed_assemble", "embed_assemble_bwd", "text_embed", "text_embed_bwd", "argmax_i64", "gather_rows",
            "l2norm_fwd", "l2norm_bwd", "clip_loss_fwd", "clip_loss_bwd", "flash_attn_fwd", "flash_attn_fwd_dyn", "gemm_skinny",
-           "ssl_clip_loss_fwd", "ssl_clip_loss_bwd")
+           "ssl_clip_loss_fwd", "ssl_clip_loss_bwd", "top_p_filter_")
+
+
+def top_p_filter_(logits, temperature, top_p):
+    """TemperatureLogitsWarper + TopPLogitsWarper(min_tokens_to_keep=1), the transformers algorithm."""
+    x = logits / temperature if temperature != 1.0 else logits.clone()
+    srt, idx = torch.sort(x, descending=False, dim=-1)
+    rm = srt.softmax(dim=-1).cumsum(dim=-1) <= (1 - top_p)
+    rm[..., -1:] = False
+    logits.copy_(x.masked_fill(rm.scatter(1, idx, rm), float("-inf")))
+    return logits
 
 
 def install(monkeypatch):

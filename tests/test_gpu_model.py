@@ -235,3 +235,56 @@ def test_clip_hf_distilbert_vs_oracle():
     assert_close_bf16(g_tp, tp.grad, "d text_projection", rel=6e-2, cos=0.99)
     assert_close_bf16(g_emb, m.textual.embeddings.word_embeddings.weight.grad, "d DistilBERT word embeddings", rel=6e-2, cos=0.99)
     assert_close_bf16(g_qkv, pr["visual.blocks.0.attn.qkv.weight"].grad, "d visual qkv", rel=6e-2, cos=0.99)
+
+
+@pytest.mark.parametrize("use_half", [False, True])
+def test_eval_zeroshot_similarity_matrix_path(use_half):
+    """The inference-only encode path of eval_zeroshot.get_similarity_matrix (eval_zeroshot.py:291-334), mirrored
+    statement by statement: model.eval() (+ model.half() / half frames with --use-half), torch.no_grad(), per batch
+    encode_image / encode_text, L2 normalisation, numpy stacking, video x text similarity; one loader yields several narrations
+    per clip (texts.ndim == 3).  Checked against the fp32 oracle: similarities to 2e-2 absolute (unit vectors), same best text
+    per video wherever the oracle's margin exceeds that tolerance."""
+    import numpy as np
+    cfg = dict(GOLD["norm"]["cfg"], depth=3)
+    params = O.init_params(cfg, seed=5)
+    model = build_clip(cfg, params)
+    K = 3                                     # narrations per clip
+    loader = []
+    for i in range(2):
+        frames, text = O.synthetic_batch(cfg, 4, seed=50 + i)
+        _, more = O.synthetic_batch(cfg, 4 * K, seed=80 + i)
+        loader.append((frames, more.view(4, K, -1)))
+
+    def similarity(encode_image, encode_text, to_dev, half):
+        vids, txts = [], []
+        with torch.no_grad():
+            for frames, texts in loader:
+                frames = to_dev(frames)
+                if half:
+                    frames = frames.half()
+                texts = to_dev(texts)
+                f = encode_image(frames)
+                f = f / f.norm(dim=-1, keepdim=True)
+                vids.append(f.float().cpu().numpy())
+                multiple = texts.ndim == 3
+                if multiple:
+                    texts = texts.view(-1, texts.shape[-1])
+                t = encode_text(texts)
+                t = t / t.norm(dim=-1, keepdim=True)
+                txts.append(t.float().cpu().numpy())
+        v, t = np.vstack(vids), np.vstack(txts)
+        sim = np.matmul(v, t.T)
+        return sim.reshape(v.shape[0], v.shape[0], -1) if multiple else sim
+
+    model.eval()
+    m = model.half() if use_half else model
+    got = similarity(m.encode_image, m.encode_text, lambda x: x.to(DEV), use_half)
+    ref = similarity(lambda fr: O.encode_image(fr, params, cfg), lambda tx: O.encode_text(tx, params, cfg), lambda x: x, False)
+    assert got.shape == ref.shape == (8, 8, K)
+    assert float(np.abs(got - ref).max()) < 2e-2, float(np.abs(got - ref).max())
+    flat_g, flat_r = got.reshape(8, -1), ref.reshape(8, -1)
+    top2 = np.sort(flat_r, axis=1)[:, -2:]
+    clear = (top2[:, 1] - top2[:, 0]) > 4e-2
+    assert (flat_g.argmax(1)[clear] == flat_r.argmax(1)[clear]).all()
+    for p in model.parameters():
+        assert p.grad is None                 # nothing recorded a graph

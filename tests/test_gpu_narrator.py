@@ -112,6 +112,39 @@ def test_kv_cached_decoding_equals_full_prefix():
     assert rel_l2(outs2[0][1], outs2[1][1]) < 1e-4
 
 
+@pytest.mark.parametrize("temperature,top_p", [(0.7, 0.95), (1.0, 0.9), (1.3, 0.5), (0.7, 0.999)])
+def test_fused_top_p_filter_keeps_the_library_token_set(temperature, top_p):
+    """lv_top_p_filter (csrc/sampling.cu) vs transformers' TemperatureLogitsWarper + TopPLogitsWarper on real decoder logits, a
+    peaked synthetic distribution and a distribution with exact ties: same -inf mask (index op), same scaled logits elsewhere."""
+    from lavila_b200 import ops
+    cfg, m, frames = _setup()
+    tok = m.encode_image(frames)
+    ids = GOLD["text"][:, :4].contiguous().to(DEV)
+    real = m.text_decoder(ids, encoder_hidden_states=tok, last_only=True).logits[:, -1, :].float()
+    g = torch.Generator(device="cpu").manual_seed(3)
+    peaked = (torch.randn(5, 50257, generator=g) * 4.0).to(DEV)
+    ties = torch.randint(-3, 4, (3, 4001), generator=g).float().to(DEV)          # many exactly equal logits
+    for x in (real, peaked, ties):
+        ref = m._get_logits_warper(top_p=top_p, temperature=temperature, num_beams=1)(None, x.clone())
+        got = ops.top_p_filter_(x.clone().contiguous(), temperature, top_p)
+        kept_ref, kept_got = ~torch.isinf(ref), ~torch.isinf(got)
+        if x is ties:
+            # which of the tied tokens at the threshold go is the sort's choice: same COUNT per row, same kept values
+            assert torch.equal(kept_ref.sum(1), kept_got.sum(1))
+            assert torch.equal(torch.sort(ref, dim=1).values, torch.sort(got, dim=1).values)
+        else:
+            # The threshold token is decided by comparing a cumulative fp32 sum with 1 - top_p; the library sums in sorted order,
+            # the kernel per radix bin, so a token whose own probability is below the round-off of that sum (top_p = 0.999: the
+            # boundary sits among tokens of probability ~1e-7) may fall on the other side: at most one token per row, and only
+            # such a negligible one.  At the script's top_p = 0.95 the masks are identical.
+            diff = kept_ref ^ kept_got
+            assert int(diff.sum(1).max()) <= (1 if top_p > 0.99 else 0), (int(kept_ref.sum()), int(kept_got.sum()))
+            probs = torch.softmax(x / temperature, dim=-1)
+            assert float(probs[diff].max() if bool(diff.any()) else 0.0) < 1e-5
+            both = kept_ref & kept_got
+            assert torch.equal(ref[both], got[both])
+
+
 def test_beam_decoding_on_the_kernels():
     """beam_sample / group_beam_search (narrator.py:149-366) on the CUDA path.  Host logic is pinned exactly on CPU
     (tests/test_host_narrator_cpu.py); here: shapes / dtypes, and the returned score of every open-ended sequence equals the
