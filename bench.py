@@ -398,16 +398,17 @@ def gemm_roofline(step_fn, ops, torch):
         c[2] += f
     by_class = [{"a_mn": k[0], "b_mn": k[1], "flags": k[2], "M": k[3], "N": k[4], "K": k[5], "launches": v[0], "ms": round(v[1], 3),
                  "tflops": round(v[2] / (v[1] / 1e3) / 1e12, 1)} for k, v in sorted(cls.items(), key=lambda kv: -kv[1][1])[:14]]
-    traffic, traffic_note = None, None
+    traffic, traffic_note, traffic_extra = None, None, {}
     try:   # DRAM bytes per launch from the committed ncu --set full capture of the same kernel (profiles/)
         cand = sorted(f for f in os.listdir(os.path.join(ROOT, "profiles")) if f.startswith("gemm_traffic_r") and f.endswith(".json"))
         t = json.load(open(os.path.join(ROOT, "profiles", cand[-1])))
         traffic, traffic_note = t["mean_dram_bytes_per_launch"], t["source"]
+        traffic_extra = {k: t[k] for k in ("kernel", "algorithmic_bytes_per_launch", "ratio") if k in t}
     except Exception:
         pass
     return {"bound": "tensor", "kernel": "lv::gemm2::gemm2_bf16_kernel (tcgen05 cta_group::2, all %d GEMM launches of one step)" % len(rec),
             "achieved": round(ach, 1), "peak": peak, "unit": "TFLOP/s", "frac": round(ach / peak, 4), "traffic": traffic,
-            "traffic_source": traffic_note, "flops_per_launch": tot_fl / max(1, len(rec)),
+            "traffic_source": traffic_note, "traffic_of": traffic_extra, "flops_per_launch": tot_fl / max(1, len(rec)),
             "peak_source": which, "flops_per_step": tot_fl, "gemm_ms_per_step": round(tot_ms, 3), "by_class": by_class}
 
 
