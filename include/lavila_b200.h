@@ -155,6 +155,16 @@ int lv_flash_attn_fwd_dyn(const void* q, int64_t ld_q, int64_t q_rows, const voi
                           const int32_t* lk_dev, int causal, float scale, void* stream);
 /* Debug: device buffer (>= 256 int64) receiving clock64() phase stamps of CTA 0 of lv_space_attn_bwd_tc; NULL disables. */
 int lv_debug_set_buffer(void* buf);
+/* Space attention INCLUDING the CLS query row in one pass (VarAttention.forward of the space half, timesformer.py:116-134): the
+ * clip's CLS query rides as an extra row of every frame's Q tile.  fwd: cls_part = fp32 scratch [B*H*T*66]; bwd: dcls_kv fp32
+ * [B][H][2][64] and dcls_q fp32 [B][H][64] zeroed by the caller; every row of out / lse / dqkv (CLS rows included) is written.
+ * 129 <= n <= 207.  Replace lv_space_attn_fwd_tc + lv_cls_attn_fwd and lv_space_attn_bwd_tc + lv_cls_attn_bwd +
+ * lv_cls_kv_finalize (which stream K, V, dK, dV of all tokens a second time). */
+int lv_space_attn_fwd_tc_cls(const void* qkv, int64_t ld_qkv, void* out, int64_t ld_out, float* lse, float* cls_part, int B,
+                             int H, int T, int n, void* stream);
+int lv_space_attn_bwd_tc_cls(const void* qkv, int64_t ld_qkv, const void* out, int64_t ld_out, const float* lse,
+                             const void* dout, int64_t ld_dout, void* dqkv, int64_t ld_dqkv, float* dcls_kv, float* dcls_q,
+                             int B, int H, int T, int n, void* stream);
 int lv_cls_attn_fwd(const void* qkv, int64_t ld_qkv, void* out, int64_t ld_out, float* lse, int B, int H, int N,
                     void* stream);
 int lv_cls_attn_bwd(const void* qkv, int64_t ld_qkv, const void* out, int64_t ld_out, const void* dout, int64_t ld_dout,

@@ -37,6 +37,10 @@ struct Params {
   __nv_bfloat16* out;
   long long ld_out;
   float* lse;
+  // CLS-query fusion (optional): the clip's CLS query rides as row n of the Q tile; its attention over THIS frame's keys
+  // (the CLS key itself counted in frame 0 only) leaves the kernel as a partial (max, sum, unnormalised output[64]) per
+  // (clip, head, frame) in cls_part [B*H*T][66]; cls_combine_kernel merges the T partials into the CLS output row / lse.
+  float* cls_part;
   int H, D, n, T;
   long long clip_rows;
   long long num_groups;
@@ -134,6 +138,10 @@ space_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const Param
       if (lane < 8) {  // CLS key row -> row Lq of the K tile (generic proxy, swizzled by hand)
         const uint4 v = __ldg(reinterpret_cast<const uint4*>(p.qkv + c.cls_row * p.ld_qkv + p.D + c.h * HD + lane * 8));
         st_shared_v4(smem_u32(sK) + Lq * 128 + ((lane ^ (Lq & 7)) << 4), v.x, v.y, v.z, v.w);
+      } else if (lane < 16 && p.cls_part) {  // CLS query row -> row Lq of the Q tile
+        const int ch = lane - 8;
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(p.qkv + c.cls_row * p.ld_qkv + c.h * HD + ch * 8));
+        st_shared_v4(smem_u32(sQ) + Lq * 128 + ((ch ^ (Lq & 7)) << 4), v.x, v.y, v.z, v.w);
       }
       fence_proxy_async_smem();
       __syncwarp();
@@ -223,13 +231,15 @@ space_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const Param
             if (cc * 32 + j < Lk) m = fmaxf(m, __uint_as_float(r[j]));
         }
       }
+      // the CLS query row (qrow == Lq, fused mode) sees the CLS key only in frame 0: the T partials must count it once
+      const int row_Lk = (qrow == Lq && c.f != 0) ? Lk - 1 : Lk;
       {
         uint32_t r[16];
         tmem_ld_32x16(ts + 192, r);
         tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 16; ++j)
-          if (192 + j < Lk) m = fmaxf(m, __uint_as_float(r[j]));
+          if (192 + j < row_Lk) m = fmaxf(m, __uint_as_float(r[j]));
       }
       // ---- pass 2: p = exp2((s - m) * scale * log2e), row sum, bf16 P into the swizzled K-major tile
       float sum = 0.f;
@@ -269,7 +279,7 @@ space_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const Param
         float pv[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          pv[j] = (192 + j < Lk) ? ex2_fast(fmaf(__uint_as_float(r[j]), sl2, -mb)) : 0.f;
+          pv[j] = (192 + j < row_Lk) ? ex2_fast(fmaf(__uint_as_float(r[j]), sl2, -mb)) : 0.f;
           sum += pv[j];
         }
         const uint32_t atom = p_tile + 3 * 16384;
@@ -311,6 +321,15 @@ space_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const Param
                          pack_bf16x2(__uint_as_float(o1[jj * 8 + 6]) * inv, __uint_as_float(o1[jj * 8 + 7]) * inv));
         }
         p.lse[grow * p.H + c.h] = m * p.scale + logf(sum);
+      } else if (qrow == Lq && p.cls_part) {
+        float* dst = p.cls_part + (((long long)c.b * p.H + c.h) * p.T + c.f) * 66;
+        dst[0] = m;
+        dst[1] = sum;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          dst[2 + j] = __uint_as_float(o0[j]);
+          dst[34 + j] = __uint_as_float(o1[j]);
+        }
       }
     }
   }
@@ -319,6 +338,26 @@ space_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const Param
     tc_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
   }
+}
+
+// CLS output row of a clip / head from the T per-frame partials: o = sum_f w_f o_f / sum_f w_f l_f, w_f = 2^((m_f - M) s log2e)
+__global__ void __launch_bounds__(64)
+cls_combine_kernel(const float* __restrict__ part, __nv_bfloat16* __restrict__ out, long long ld_out, float* __restrict__ lse,
+                   int H, int T, long long clip_rows, float scale) {
+  const int b = blockIdx.x / H, h = blockIdx.x - b * H, d = threadIdx.x;
+  const float* pp = part + ((long long)b * H + h) * T * 66;
+  float M = -INFINITY;
+  for (int f = 0; f < T; ++f) M = fmaxf(M, pp[f * 66]);
+  const float sl2 = scale * LOG2E;
+  float L = 0.f, o = 0.f;
+  for (int f = 0; f < T; ++f) {
+    const float w = ex2_fast((pp[f * 66] - M) * sl2);
+    L += w * pp[f * 66 + 1];
+    o += w * pp[f * 66 + 2 + d];
+  }
+  const long long row = (long long)b * clip_rows;
+  out[row * ld_out + h * HD + d] = __float2bfloat16_rn(o / L);
+  if (d == 0) lse[row * H + h] = M * scale + logf(L);
 }
 
 constexpr int FWD_SMEM = 1024 + SQ_BYTES + 2 * SK_BYTES + 2 * SP_BYTES + 128;
@@ -359,6 +398,10 @@ struct BwdParams {
   __nv_bfloat16* dqkv;
   long long ld_dqkv;
   float* dcls_kv;
+  // CLS-query fusion (optional): the clip's CLS query / its output gradient ride as row n of the Q / dO tiles (lse and delta of
+  // that row come from the clip's CLS row), so dV / dK of every key receive the CLS query's contribution in the same MMAs; the
+  // per-frame partial dQ_cls is accumulated into dcls_q fp32 [B][H][64] (zeroed by the caller).  Replaces lv_cls_attn_bwd.
+  float* dcls_q;
   int accumulate_kv;
   int H, D, n, T;
   long long clip_rows;
@@ -497,6 +540,17 @@ space_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __gri
       }
     };
     auto issue_qdo = [&](int it2, const Coord& c) {
+      if (p.dcls_q) {    // fused CLS query: q_cls -> row Lq of the Q tile, dO_cls -> row Lq of the dO tile
+        if (lane < 16) {
+          const int part = lane >> 3, ch = lane & 7;
+          const __nv_bfloat16* src = part ? p.dout + c.cls_row * p.ld_dout + c.h * HD + ch * 8
+                                          : p.qkv + c.cls_row * p.ld_qkv + c.h * HD + ch * 8;
+          const uint4 v = __ldg(reinterpret_cast<const uint4*>(src));
+          st_shared_v4(smem_u32(tile_of(it2, part ? 3 : 2)) + Lq * 128 + ((ch ^ (Lq & 7)) << 4), v.x, v.y, v.z, v.w);
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+      }
       if (lane == 0) {
         mbar_arrive_expect_tx(bar_loadB, 2 * Lq * 128);
         tma_load_2d(tile_of(it2, 2), &tm_qkv, bar_loadB, c.h * HD, (int)c.base_row);
@@ -506,9 +560,10 @@ space_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __gri
     auto prep = [&](int it2, const Coord& c) {
       float* ls = s_lse + (it2 & 1) * B_VEC;
       float* dl = s_delta + (it2 & 1) * B_VEC;
+      const int nrows = Lq + (p.dcls_q ? 1 : 0);      // fused mode: entry Lq = the clip's CLS row
 #pragma unroll 1
-      for (int r = lane; r < Lq; r += 32) {
-        const long long grow = c.base_row + r;
+      for (int r = lane; r < nrows; r += 32) {
+        const long long grow = r < Lq ? c.base_row + r : c.cls_row;
         const __nv_bfloat16* orow = p.out + grow * p.ld_out + c.h * HD;
         const __nv_bfloat16* drow = p.dout + grow * p.ld_dout + c.h * HD;
         uint4 o8[8], d8[8];
@@ -717,7 +772,8 @@ space_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __gri
               } else {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                  const bool ok = key_ok && (qg + j < Lq);
+                  // fused CLS query (column Lq): every key of the frame, the CLS key itself only in frame 0
+                  const bool ok = key_ok && ((qg + j < Lq) || (p.dcls_q && qg + j == Lq && (key < Lk - 1 || c.f == 0)));
                   const float pj = ok ? ex2_fast(fmaf(__uint_as_float(s32[g8 * 8 + j]), sl2, -l8[j])) : 0.f;
                   pv[j] = pj;
                   dv[j] = ok ? pj * (__uint_as_float(d32[g8 * 8 + j]) - dl8[j]) * p.scale : 0.f;
@@ -768,6 +824,14 @@ space_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __gri
         const int qrow = hf * 128 + row;
         if (tma_out) stage_row64(ds_tile + hf * 16384, row, a, b);
         else if (qrow < Lq) store_row64(p.dqkv + (c.base_row + qrow) * p.ld_dqkv + c.h * HD, a, b, false);
+        if (qrow == Lq && p.dcls_q) {   // this frame's share of dQ of the CLS query
+          float* base = p.dcls_q + ((long long)c.b * p.H + c.h) * HD;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            atomicAdd(base + j, __uint_as_float(a[j]));
+            atomicAdd(base + 32 + j, __uint_as_float(b[j]));
+          }
+        }
       }
       tc_fence_before();
       if (tma_out) {
@@ -827,6 +891,42 @@ extern "C" int lv_space_attn_fwd_tc(const void* qkv, int64_t ld_qkv, void* out, 
   return check_launch("lv_space_attn_fwd_tc");
 }
 
+// Space attention forward INCLUDING the CLS query row (VarAttention.forward, lavila/models/timesformer.py:116-134, both halves):
+// the tcgen05 group kernel carries the clip's CLS query as an extra row of every frame's Q tile and writes one partial per
+// (clip, head, frame) into cls_part (fp32 [B*H*T*66], caller-owned scratch); cls_combine_kernel merges them.  Replaces the
+// pair lv_space_attn_fwd_tc + lv_cls_attn_fwd (which streams K and V of all tokens a second time).
+extern "C" int lv_space_attn_fwd_tc_cls(const void* qkv, int64_t ld_qkv, void* out, int64_t ld_out, float* lse, float* cls_part,
+                                        int B, int H, int T, int n, void* stream) {
+  LV_REQUIRE(qkv && out && lse && cls_part && B > 0 && H > 0 && T > 0, "lv_space_attn_fwd_tc_cls: bad arguments");
+  LV_REQUIRE(n > 128 && n + 1 <= attn_tc::KROWS, "lv_space_attn_fwd_tc_cls: n=%d unsupported (129..207)", n);
+  LV_REQUIRE(ld_qkv % 8 == 0 && ld_out % 8 == 0, "lv_space_attn_fwd_tc_cls: leading dimensions must be multiples of 8");
+  attn_tc::Params p{};
+  p.qkv = (const __nv_bfloat16*)qkv; p.ld_qkv = ld_qkv;
+  p.out = (__nv_bfloat16*)out; p.ld_out = ld_out;
+  p.lse = lse;
+  p.cls_part = cls_part;
+  p.H = H; p.D = H * attn_tc::HD; p.n = n; p.T = T;
+  p.clip_rows = 1 + (long long)T * n;
+  p.num_groups = (long long)B * H * T;
+  p.scale = 0.125f;
+  const long long rows = (long long)B * p.clip_rows;
+  CUtensorMap tm;
+  int rc = make_tmap_2d_bf16(&tm, qkv, (uint64_t)(3 * p.D), (uint64_t)rows, (uint64_t)ld_qkv, 64, (uint32_t)n);
+  if (rc) return rc;
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, []() {
+    attr_err = cudaFuncSetAttribute(attn_tc::space_attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, attn_tc::FWD_SMEM);
+  });
+  if (attr_err != cudaSuccess) return set_error((int)attr_err, "lv_space_attn_fwd_tc_cls: cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err));
+  const long long grid = p.num_groups < sm_count() ? p.num_groups : sm_count();
+  attn_tc::space_attn_fwd_tc_kernel<<<(unsigned)grid, attn_tc::NTHREADS, attn_tc::FWD_SMEM, (cudaStream_t)stream>>>(tm, p);
+  rc = check_launch("lv_space_attn_fwd_tc_cls");
+  if (rc) return rc;
+  attn_tc::cls_combine_kernel<<<B * H, 64, 0, (cudaStream_t)stream>>>(cls_part, (__nv_bfloat16*)out, ld_out, lse, H, T, p.clip_rows, p.scale);
+  return check_launch("lv_space_attn_fwd_tc_cls(combine)");
+}
+
 // Space attention backward on tcgen05.  Same contract / call order as lv_group_attn_bwd(mode 0):
 // lv_cls_attn_bwd -> lv_space_attn_bwd_tc(accumulate_kv = 1) -> lv_cls_kv_finalize.
 extern "C" int lv_space_attn_bwd_tc(const void* qkv, int64_t ld_qkv, const void* out, int64_t ld_out, const float* lse,
@@ -866,6 +966,63 @@ extern "C" int lv_space_attn_bwd_tc(const void* qkv, int64_t ld_qkv, const void*
   const long long grid = p.num_groups < sm_count() ? p.num_groups : sm_count();
   attn_tc::space_attn_bwd_tc_kernel<<<(unsigned)grid, attn_tc::NTHREADS, attn_tc::BWD_SMEM, (cudaStream_t)stream>>>(tm_qkv, tm_do, tm_st128, tm_sttail, p);
   return check_launch("lv_space_attn_bwd_tc");
+}
+
+namespace lv {
+namespace attn_tc {
+// dqkv[cls row] = bf16([dq_cls | dk_cls | dv_cls]) from the fp32 accumulators
+__global__ void cls_qkv_finalize_kernel(const float* __restrict__ dcls_kv, const float* __restrict__ dcls_q,
+                                        __nv_bfloat16* __restrict__ dqkv, long long lddq, int H, int D, long long N) {
+  const int b = blockIdx.x / H, h = blockIdx.x - b * H;
+  const int part = threadIdx.x >> 6, d = threadIdx.x & 63;       // 192 threads: [q 64 | k 64 | v 64]
+  const float v = part == 0 ? dcls_q[((long long)b * H + h) * HD + d] : dcls_kv[(((long long)b * H + h) * 2 + (part - 1)) * HD + d];
+  dqkv[(long long)b * N * lddq + part * D + h * HD + d] = __float2bfloat16_rn(v);
+}
+}  // namespace attn_tc
+}  // namespace lv
+
+// Space attention backward INCLUDING the CLS query (pairs with lv_space_attn_fwd_tc_cls): one tcgen05 kernel + a 3 x 64-value
+// finalize per (clip, head).  dcls_kv fp32 [B][H][2][64] and dcls_q fp32 [B][H][64] are zeroed scratch of the caller; every row
+// of dqkv (CLS rows included) is overwritten.  Replaces lv_space_attn_bwd_tc + lv_cls_attn_bwd + lv_cls_kv_finalize.
+extern "C" int lv_space_attn_bwd_tc_cls(const void* qkv, int64_t ld_qkv, const void* out, int64_t ld_out, const float* lse,
+                                        const void* dout, int64_t ld_dout, void* dqkv, int64_t ld_dqkv, float* dcls_kv,
+                                        float* dcls_q, int B, int H, int T, int n, void* stream) {
+  LV_REQUIRE(qkv && out && lse && dout && dqkv && dcls_kv && dcls_q && B > 0 && H > 0 && T > 0, "lv_space_attn_bwd_tc_cls: bad arguments");
+  LV_REQUIRE(n > 128 && n + 1 <= attn_tc::KROWS, "lv_space_attn_bwd_tc_cls: n=%d unsupported (129..207)", n);
+  LV_REQUIRE(ld_qkv % 8 == 0 && ld_out % 8 == 0 && ld_dout % 8 == 0 && ld_dqkv % 8 == 0, "lv_space_attn_bwd_tc_cls: leading dimensions must be multiples of 8");
+  attn_tc::BwdParams p{};
+  p.qkv = (const __nv_bfloat16*)qkv; p.ld_qkv = ld_qkv;
+  p.out = (const __nv_bfloat16*)out; p.ld_out = ld_out;
+  p.dout = (const __nv_bfloat16*)dout; p.ld_dout = ld_dout;
+  p.lse = lse;
+  p.dqkv = (__nv_bfloat16*)dqkv; p.ld_dqkv = ld_dqkv;
+  p.dcls_kv = dcls_kv; p.dcls_q = dcls_q; p.accumulate_kv = 0;
+  p.H = H; p.D = H * attn_tc::HD; p.n = n; p.T = T;
+  p.clip_rows = 1 + (long long)T * n;
+  p.num_groups = (long long)B * H * T;
+  p.scale = 0.125f;
+  const long long rows = (long long)B * p.clip_rows;
+  CUtensorMap tm_qkv, tm_do, tm_st128, tm_sttail;
+  int rc = make_tmap_2d_bf16(&tm_qkv, qkv, (uint64_t)(3 * p.D), (uint64_t)rows, (uint64_t)ld_qkv, 64, (uint32_t)n);
+  if (rc) return rc;
+  rc = make_tmap_2d_bf16(&tm_do, dout, (uint64_t)p.D, (uint64_t)rows, (uint64_t)ld_dout, 64, (uint32_t)n);
+  if (rc) return rc;
+  rc = make_tmap_2d_bf16(&tm_st128, dqkv, (uint64_t)(3 * p.D), (uint64_t)rows, (uint64_t)ld_dqkv, 64, 128);
+  if (rc) return rc;
+  rc = make_tmap_2d_bf16(&tm_sttail, dqkv, (uint64_t)(3 * p.D), (uint64_t)rows, (uint64_t)ld_dqkv, 64, (uint32_t)(n - 128));
+  if (rc) return rc;
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, []() {
+    attr_err = cudaFuncSetAttribute(attn_tc::space_attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, attn_tc::BWD_SMEM);
+  });
+  if (attr_err != cudaSuccess) return set_error((int)attr_err, "lv_space_attn_bwd_tc_cls: cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err));
+  const long long grid = p.num_groups < sm_count() ? p.num_groups : sm_count();
+  attn_tc::space_attn_bwd_tc_kernel<<<(unsigned)grid, attn_tc::NTHREADS, attn_tc::BWD_SMEM, (cudaStream_t)stream>>>(tm_qkv, tm_do, tm_st128, tm_sttail, p);
+  rc = check_launch("lv_space_attn_bwd_tc_cls");
+  if (rc) return rc;
+  attn_tc::cls_qkv_finalize_kernel<<<B * H, 192, 0, (cudaStream_t)stream>>>(dcls_kv, dcls_q, (__nv_bfloat16*)dqkv, ld_dqkv, H, p.D, p.clip_rows);
+  return check_launch("lv_space_attn_bwd_tc_cls(finalize)");
 }
 
 extern "C" int lv_debug_set_buffer(void* buf) {

@@ -168,6 +168,8 @@ def attn_sub_fwd(x_ln, resid, P, dims, mode, eps, gate=None):
     lse = torch.empty(M, H, device=dev, dtype=F32)
     if mode == MODE_CAUSAL:
         ops.group_attn_fwd(qkv, att, lse, mode, B, H, Lctx=dims["L"])
+    elif mode == MODE_SPACE and ops.space_attn_cls_fused_supported(dims["n"]):
+        ops.space_attn_fwd_cls(qkv, att, lse, B, H, dims["T"], dims["n"])        # CLS query inside the tcgen05 group kernel
     else:
         ops.group_attn_fwd(qkv, att, lse, mode, B, H, T=dims["T"], n=dims["n"])
         ops.cls_attn_fwd(qkv, att, lse, B, H, dims["N"])
@@ -210,6 +212,8 @@ def attn_sub_bwd(dy, dy_b, P, S, adds=(), want_bf16=True):
     dqkv = torch.empty(M, 3 * D, device=dev, dtype=BF16)
     if mode == MODE_CAUSAL:
         ops.group_attn_bwd(S["qkv"], S["att"], S["lse"], datt, dqkv, None, 0, mode, B, H, Lctx=dims["L"])
+    elif mode == MODE_SPACE and ops.space_attn_cls_fused_supported(dims["n"]):
+        ops.space_attn_bwd_cls(S["qkv"], S["att"], S["lse"], datt, dqkv, B, H, dims["T"], dims["n"])
     else:
         # group kernel first (plain stores), then the streaming CLS-query kernel accumulates on top: keeps the
         # read-modify-write latency out of the tensor-core kernel's critical path
@@ -747,8 +751,11 @@ class VarAttentionFn(torch.autograd.Function):
         ops.gemm(xb, SHADOW.get(qkv_w), M, 3 * D, D, qkv, flags=L.EPI_BIAS, bias=qkv_b)
         att = torch.empty(M, D, device=dev, dtype=BF16)
         lse = torch.empty(M, heads, device=dev, dtype=F32)
-        ops.group_attn_fwd(qkv, att, lse, mode, B, heads, T=frames, n=patches)
-        ops.cls_attn_fwd(qkv, att, lse, B, heads, N)
+        if mode == MODE_SPACE and ops.space_attn_cls_fused_supported(patches):
+            ops.space_attn_fwd_cls(qkv, att, lse, B, heads, frames, patches)
+        else:
+            ops.group_attn_fwd(qkv, att, lse, mode, B, heads, T=frames, n=patches)
+            ops.cls_attn_fwd(qkv, att, lse, B, heads, N)
         y = torch.empty(M, D, device=dev, dtype=F32)
         ops.gemm(att, SHADOW.get(proj_w), M, D, D, y, flags=L.EPI_BIAS, bias=proj_b)
         ctx.saved = (xb, qkv, att, lse, qkv_w, qkv_b, proj_w, proj_b)
@@ -769,10 +776,13 @@ class VarAttentionFn(torch.autograd.Function):
         datt = torch.empty(M, D, device=dev, dtype=BF16)
         ops.gemm(dyb, SHADOW.get(proj_w), M, D, D, datt, b_mn=1)
         dqkv = torch.empty(M, 3 * D, device=dev, dtype=BF16)
-        dcls = torch.zeros(B, heads, 2, 64, device=dev, dtype=F32)
-        ops.group_attn_bwd(qkv, att, lse, datt, dqkv, dcls, 0, mode, B, heads, T=frames, n=patches)
-        ops.cls_attn_bwd(qkv, att, datt, lse, dqkv, dcls, B, heads, N, accumulate=True)
-        ops.cls_kv_finalize(dcls, dqkv, B, heads, N)
+        if mode == MODE_SPACE and ops.space_attn_cls_fused_supported(patches):
+            ops.space_attn_bwd_cls(qkv, att, lse, datt, dqkv, B, heads, frames, patches)
+        else:
+            dcls = torch.zeros(B, heads, 2, 64, device=dev, dtype=F32)
+            ops.group_attn_bwd(qkv, att, lse, datt, dqkv, dcls, 0, mode, B, heads, T=frames, n=patches)
+            ops.cls_attn_bwd(qkv, att, datt, lse, dqkv, dcls, B, heads, N, accumulate=True)
+            ops.cls_kv_finalize(dcls, dqkv, B, heads, N)
         d_qw, d_qb = _zeros_like_param(qkv_w), _zeros_like_param(qkv_b)
         _wgrad(dqkv, xb, 3 * D, D, M, d_qw)
         ops.colsum_bf16(dqkv, M, 3 * D, d_qb)

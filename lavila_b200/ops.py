@@ -151,6 +151,32 @@ def group_attn_bwd(qkv, out, lse, dout, dqkv, dcls_kv, accumulate_kv, mode, B, H
     L.check(rc, "lv_group_attn_bwd")
 
 
+import os as _os
+USE_TC_CLS_FUSION = _os.environ.get("LAVILA_B200_CLS_FUSION", "1") == "1"   # space attention: the CLS query rides inside the tcgen05 group kernels
+
+
+def space_attn_cls_fused_supported(n):
+    return USE_TC_CLS_FUSION and USE_TC_ATTN_FWD and USE_TC_ATTN_BWD and space_attn_tc_supported(n)
+
+
+def space_attn_fwd_cls(qkv, out, lse, B, H, T, n):
+    """Space attention forward for every row, CLS rows included (lv_space_attn_fwd_tc_cls)."""
+    part = torch.empty(B * H * T * 66, device=qkv.device, dtype=F32)
+    rc = L.lib().lv_space_attn_fwd_tc_cls(qkv.data_ptr(), qkv.stride(0), out.data_ptr(), out.stride(0), lse.data_ptr(),
+                                          part.data_ptr(), B, H, T, n, _stream())
+    L.check(rc, "lv_space_attn_fwd_tc_cls")
+
+
+def space_attn_bwd_cls(qkv, out, lse, dout, dqkv, B, H, T, n):
+    """Space attention backward for every row, CLS rows included (lv_space_attn_bwd_tc_cls)."""
+    scratch = torch.zeros(B * H * 3 * 64, device=qkv.device, dtype=F32)
+    dkv, dq = scratch[:B * H * 128], scratch[B * H * 128:]
+    rc = L.lib().lv_space_attn_bwd_tc_cls(qkv.data_ptr(), qkv.stride(0), out.data_ptr(), out.stride(0), lse.data_ptr(),
+                                          dout.data_ptr(), dout.stride(0), dqkv.data_ptr(), dqkv.stride(0), dkv.data_ptr(),
+                                          dq.data_ptr(), B, H, T, n, _stream())
+    L.check(rc, "lv_space_attn_bwd_tc_cls")
+
+
 def flash_attn_fwd(q, k, v, out, B, H, Lq, Lk, *, q_rows, kv_rows, ld_q, ld_kv, ld_out, kv_head_stride=64, causal=False,
                    scale=0.125):
     rc = L.lib().lv_flash_attn_fwd(q.data_ptr(), ld_q, q_rows, k.data_ptr(), v.data_ptr(), ld_kv, kv_rows, kv_head_stride,

@@ -423,7 +423,8 @@ DOUBLES = ("gemm", "wgrad_splits", "layernorm_fwd", "layernorm_bwd", "group_attn
            "cls_attn_bwd", "cls_kv_finalize", "cls_query_attn_fwd", "cls_query_attn_bwd", "add_rows", "cast_bf16", "colsum_bf16",
            "patch_im2col", "embed_assemble", "embed_assemble_bwd", "text_embed", "text_embed_bwd", "argmax_i64", "gather_rows",
            "l2norm_fwd", "l2norm_bwd", "clip_loss_fwd", "clip_loss_bwd", "flash_attn_fwd", "flash_attn_fwd_dyn", "gemm_skinny",
-           "ssl_clip_loss_fwd", "ssl_clip_loss_bwd", "top_p_filter_")
+           "ssl_clip_loss_fwd", "ssl_clip_loss_bwd", "top_p_filter_",
+           "space_attn_cls_fused_supported", "space_attn_fwd_cls", "space_attn_bwd_cls")
 
 
 def top_p_filter_(logits, temperature, top_p):
@@ -434,6 +435,23 @@ def top_p_filter_(logits, temperature, top_p):
     rm[..., -1:] = False
     logits.copy_(x.masked_fill(rm.scatter(1, idx, rm), float("-inf")))
     return logits
+
+
+def space_attn_cls_fused_supported(n):
+    return 128 < n <= 207
+
+
+def space_attn_fwd_cls(qkv, out, lse, B, H, T, n):
+    """Contract of lv_space_attn_fwd_tc_cls: the group pass and the CLS-query pass of the space attention, every row written."""
+    group_attn_fwd(qkv, out, lse, 0, B, H, T=T, n=n)
+    cls_attn_fwd(qkv, out, lse, B, H, 1 + T * n)
+
+
+def space_attn_bwd_cls(qkv, out, lse, dout, dqkv, B, H, T, n):
+    dcls = torch.zeros(B, H, 2, 64)
+    group_attn_bwd(qkv, out, lse, dout, dqkv, dcls, 0, 0, B, H, T=T, n=n)
+    cls_attn_bwd(qkv, out, dout, lse, dqkv, dcls, B, H, 1 + T * n, accumulate=True)
+    cls_kv_finalize(dcls, dqkv, B, H, 1 + T * n)
 
 
 def install(monkeypatch):
