@@ -2,6 +2,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <mutex>
 
 #include "../../include/lavila_b200.h"
@@ -37,6 +38,14 @@ int sm_count() {
   std::call_once(once[dev], [dev]() {
     int n = 0;
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    // LAVILA_B200_RESERVE_SMS=k: the persistent kernels (one CTA per SM, all of its shared memory) size their grids for n - k
+    // SMs, leaving k SMs to concurrent work of other streams -- NCCL's all-reduce CTAs under DistributedDataParallel cannot
+    // co-reside with a 227 KB CTA and otherwise only run between our kernels.  Even count (CTA pairs).  Default 0.
+    if (const char* e = std::getenv("LAVILA_B200_RESERVE_SMS")) {
+      int k = atoi(e);
+      k = (k / 2) * 2;
+      if (k > 0 && k < n / 2) n -= k;
+    }
     cached[dev] = n;
   });
   return cached[dev];
