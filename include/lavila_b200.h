@@ -165,6 +165,13 @@ int lv_space_attn_fwd_tc_cls(const void* qkv, int64_t ld_qkv, void* out, int64_t
 int lv_space_attn_bwd_tc_cls(const void* qkv, int64_t ld_qkv, const void* out, int64_t ld_out, const float* lse,
                              const void* dout, int64_t ld_dout, void* dqkv, int64_t ld_dqkv, float* dcls_kv, float* dcls_q,
                              int B, int H, int T, int n, void* stream);
+/* Time attention (<= 16 frames per group) INCLUDING the CLS query row: as lv_space_attn_*_tc_cls with one partial per
+ * (clip, head, spatial position): cls_part = fp32 scratch [B*H*n*66]. */
+int lv_time_attn_fwd_cls(const void* qkv, int64_t ld_qkv, void* out, int64_t ld_out, float* lse, float* cls_part, int B, int H,
+                         int T, int n, void* stream);
+int lv_time_attn_bwd_cls(const void* qkv, int64_t ld_qkv, const void* out, int64_t ld_out, const float* lse, const void* dout,
+                         int64_t ld_dout, void* dqkv, int64_t ld_dqkv, float* dcls_kv, float* dcls_q, int B, int H, int T, int n,
+                         void* stream);
 int lv_cls_attn_fwd(const void* qkv, int64_t ld_qkv, void* out, int64_t ld_out, float* lse, int B, int H, int N,
                     void* stream);
 int lv_cls_attn_bwd(const void* qkv, int64_t ld_qkv, const void* out, int64_t ld_out, const void* dout, int64_t ld_dout,

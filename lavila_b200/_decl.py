@@ -11,6 +11,8 @@ SIGNATURES = {
     "lv_space_attn_fwd_tc": [P, L, P, L, P, I, I, I, I, P],
     "lv_space_attn_bwd_tc": [P, L, P, L, P, P, L, P, L, P, I, I, I, I, I, P],
     "lv_space_attn_fwd_tc_cls": [P, L, P, L, P, P, I, I, I, I, P],
+    "lv_time_attn_fwd_cls": [P, L, P, L, P, P, I, I, I, I, P],
+    "lv_time_attn_bwd_cls": [P, L, P, L, P, P, L, P, L, P, P, I, I, I, I, P],
     "lv_space_attn_bwd_tc_cls": [P, L, P, L, P, P, L, P, L, P, P, I, I, I, I, P],
     "lv_flash_attn_fwd": [P, L, L, P, P, L, L, I, P, L, I, I, I, I, I, F, P],
     "lv_flash_attn_fwd_dyn": [P, L, L, P, P, L, L, I, P, L, I, I, I, P, I, F, P],

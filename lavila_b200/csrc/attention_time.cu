@@ -26,8 +26,9 @@ constexpr int Q_TILE = 16 * ROW_BYTES;         // 16 query rows
 constexpr int KV_TILE = 17 * ROW_BYTES;        // 16 token rows + the CLS row
 constexpr int FWD_STAGE = Q_TILE + 2 * KV_TILE;
 constexpr int BWD_STAGE = 2 * Q_TILE + 2 * KV_TILE;
-constexpr int FWD_WARP_BYTES = 2 * FWD_STAGE;
-constexpr int BWD_WARP_BYTES = 2 * BWD_STAGE + 128;   // + delta[16] fp32 (padded)
+constexpr int CLS_SCRATCH = 256;                      // q_cls [64] bf16 | dO_cls [64] bf16 of the warp's (clip, head) (fused CLS query)
+constexpr int FWD_WARP_BYTES = 2 * FWD_STAGE + CLS_SCRATCH;
+constexpr int BWD_WARP_BYTES = 2 * BWD_STAGE + 128 + CLS_SCRATCH;   // + delta[16] fp32 (padded)
 
 struct Params {
   const __nv_bfloat16* qkv; long long ld_qkv;
@@ -36,6 +37,14 @@ struct Params {
   const __nv_bfloat16* dout; long long ld_dout;
   __nv_bfloat16* dqkv; long long ld_dqkv;
   float* dcls_kv;
+  // CLS-query fusion (optional).  The clip's CLS query attends to every token (timesformer.py:116-119); its attention over the
+  // <= 16 keys of a unit (the CLS key counted in the unit of spatial position 0 only) is evaluated next to the group:
+  //   forward : partial (max, sum, unnormalised output[64]) per (clip, head, position) -> cls_part [B*H*n][66], merged by
+  //             time_cls_combine_kernel;
+  //   backward: the CLS query's contribution is added to the unit's dV / dK fragments before they are stored, dQ_cls is
+  //             accumulated in registers over the units of a clip and flushed into dcls_q fp32 [B][H][64].
+  float* cls_part;
+  float* dcls_q;
   int H, D, Lq, n, hc, hchunks;
   long long clip_rows;
   int units;                                     // B * hchunks * n
@@ -117,6 +126,38 @@ __device__ __forceinline__ void load_rows(uint32_t tile, int Lq, const __nv_bflo
   if (cls_ptr && lane < 8) cp_async16(tile + swz(16, lane), cls_ptr + lane * 8);
 }
 
+// lane = (key = lane & 15, half = lane >> 4): partial dot of tile row `key` with a 64-element bf16 vector over its 32-element half
+__device__ __forceinline__ float half_row_dot(uint32_t tile, int key, int half, uint32_t vec) {
+  float acc = 0.f;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const uint4 a = ld_shared_v4(tile + swz(key, half * 4 + c));
+    const uint4 b = ld_shared_v4(vec + (half * 4 + c) * 16);
+    const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 x = unpack_bf16x2(aw[j]), y = unpack_bf16x2(bw[j]);
+      acc += x.x * y.x + x.y * y.y;
+    }
+  }
+  return acc + __shfl_xor_sync(0xffffffffu, acc, 16);
+}
+__device__ __forceinline__ float warp_max16(float v) {   // over the 16 lanes that share (lane >> 4)
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_sum16(float v) {
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float2 ld_shared_bf16x2(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return unpack_bf16x2(v);
+}
+
 // C-fragment tile (16 rows x 64 cols fp32) -> bf16 staging tile -> global rows (128 bytes per row, coalesced)
 __device__ __forceinline__ void stage_and_store(uint32_t tile, float (&acc)[8][4], int Lq, __nv_bfloat16* dst, long long ld,
                                                 long long base_row, long long row_stride, int lane) {
@@ -159,6 +200,8 @@ time_attn_fwd_kernel(const Params p) {
     __syncwarp();
   }
   const long long rs = p.n;
+  const uint32_t sCls = ws + 2 * FWD_STAGE;     // q_cls of the current (clip, head)
+  int cls_bh = -1;
   auto issue = [&](int u, int st) {
     const Unit c = decode(p, u, warp);
     const uint32_t sQ = ws + st * FWD_STAGE, sK = sQ + Q_TILE, sV = sK + KV_TILE;
@@ -240,6 +283,45 @@ time_attn_fwd_kernel(const Params p) {
     const float inv0 = g < p.Lq ? 1.f / sum0 : 0.f, inv1 = g + 8 < p.Lq ? 1.f / sum1 : 0.f;
 #pragma unroll
     for (int dt = 0; dt < 8; ++dt) { o[dt][0] *= inv0; o[dt][1] *= inv0; o[dt][2] *= inv1; o[dt][3] *= inv1; }
+    if (p.cls_part) {
+      // ---- fused CLS query: partial attention of q_cls over this unit's keys (+ the CLS key in the unit of position 0)
+      if (c.bh != cls_bh) {
+        cls_bh = c.bh;
+        __syncwarp();
+        if (lane < 8) {
+          const uint4 v = __ldg(reinterpret_cast<const uint4*>(p.qkv + c.cls_row * p.ld_qkv + c.h * HD + lane * 8));
+          asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(sCls + lane * 16), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+        }
+        __syncwarp();
+      }
+      const int key = lane & 15, half = lane >> 4;
+      const bool first = (c.base_row - c.cls_row) == 1;                   // spatial position 0: this unit also owns the CLS key
+      float sc = half_row_dot(sK, key, half, sCls);
+      const float scc = half_row_dot(sK, 16, half, sCls);                 // q_cls . k_cls
+      sc = key < p.Lq ? sc : -INFINITY;
+      float mc = warp_max16(sc);
+      if (first) mc = fmaxf(mc, scc);
+      const float pc = exp2f((sc - mc) * sl2);                            // exp2(-inf) = 0 for the masked slots
+      const float pcc = first ? exp2f((scc - mc) * sl2) : 0.f;
+      const float lc = warp_sum16(pc) + pcc;
+      float oc0 = 0.f, oc1 = 0.f;                                         // columns 2 * lane, 2 * lane + 1
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float pj = __shfl_sync(0xffffffffu, pc, j);
+        const float2 v = ld_shared_bf16x2(sV + swz(j, lane >> 2) + (lane & 3) * 4);
+        oc0 = fmaf(pj, v.x, oc0);
+        oc1 = fmaf(pj, v.y, oc1);
+      }
+      {
+        const float2 v = ld_shared_bf16x2(sV + swz(16, lane >> 2) + (lane & 3) * 4);
+        oc0 = fmaf(pcc, v.x, oc0);
+        oc1 = fmaf(pcc, v.y, oc1);
+      }
+      const long long pos = (c.base_row - c.cls_row - 1);
+      float* dst = p.cls_part + (((c.cls_row / p.clip_rows) * p.H + c.h) * (long long)p.n + pos) * 66;
+      if (lane == 0) { dst[0] = mc; dst[1] = lc; }
+      *reinterpret_cast<float2*>(dst + 2 + 2 * lane) = make_float2(oc0, oc1);
+    }
     stage_and_store(sQ, o, p.Lq, p.out + c.h * HD, p.ld_out, c.base_row, rs, lane);
     if (t == 0) {
       if (g < p.Lq) p.lse[(c.base_row + (long long)g * rs) * p.H + c.h] = m0 * p.scale + logf(sum0);
@@ -293,6 +375,19 @@ time_attn_bwd_kernel(const Params p) {
     }
     lse_next[0] = g < p.Lq ? __ldg(p.lse + (c.base_row + (long long)g * rs) * p.H + c.h) * LOG2E : 0.f;
     lse_next[1] = g + 8 < p.Lq ? __ldg(p.lse + (c.base_row + (long long)(g + 8) * rs) * p.H + c.h) * LOG2E : 0.f;
+  };
+  // fused CLS query (p.dcls_q): q_cls | dO_cls of the current (clip, head) in the warp's scratch, lse / delta of the CLS row,
+  // this lane's two columns of dQ_cls accumulated over the units of the clip
+  const uint32_t sClsQ = ws + 2 * BWD_STAGE + 128, sClsDo = sClsQ + 128;
+  int cls_bh = -1;
+  float lse_c = 0.f, delta_c = 0.f, dqc0 = 0.f, dqc1 = 0.f;
+  auto flush_dq = [&](const Unit& c) {
+    if (p.dcls_q) {
+      float* base = p.dcls_q + ((long long)(c.bh / p.hchunks) * p.H + c.h) * HD;
+      atomicAdd(base + 2 * lane, dqc0);
+      atomicAdd(base + 2 * lane + 1, dqc1);
+      dqc0 = dqc1 = 0.f;
+    }
   };
   float clsk[8][2], clsv[8][2];   // CLS key/value gradient of this warp's head, rows of lanes 0-3 only
 #pragma unroll
@@ -405,6 +500,66 @@ time_attn_bwd_kernel(const Params p) {
       }
     }
     if (u + 1 < u1) fetch_o(nxt);   // in flight during the gradient MMAs and stores below
+    float Pc = 0.f, dSc = 0.f, Pcc = 0.f, dScc = 0.f;     // CLS query x (key lane & 15 | the CLS key)
+    if (p.dcls_q) {
+      if (cur.bh != cls_bh) {
+        cls_bh = cur.bh;
+        __syncwarp();
+        if (lane < 16) {
+          const int part = lane >> 3, ch = lane & 7;
+          const __nv_bfloat16* src = part ? p.dout + cur.cls_row * p.ld_dout + cur.h * HD + ch * 8
+                                          : p.qkv + cur.cls_row * p.ld_qkv + cur.h * HD + ch * 8;
+          const uint4 v = __ldg(reinterpret_cast<const uint4*>(src));
+          asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"((part ? sClsDo : sClsQ) + ch * 16), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+        }
+        __syncwarp();
+        // delta of the CLS row = dO_cls . O_cls ; lse in log2 units
+        const float2 oc = unpack_bf16x2(__ldg(reinterpret_cast<const unsigned int*>(p.out + cur.cls_row * p.ld_out + cur.h * HD + 2 * lane)));
+        const float2 dc = ld_shared_bf16x2(sClsDo + lane * 4);
+        float part = oc.x * dc.x + oc.y * dc.y;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+        delta_c = part;
+        lse_c = __ldg(p.lse + cur.cls_row * p.H + cur.h) * LOG2E;
+      }
+      const int key = lane & 15, half = lane >> 4;
+      const bool first = (cur.base_row - cur.cls_row) == 1;
+      const float sc = half_row_dot(sK, key, half, sClsQ), dpc = half_row_dot(sV, key, half, sClsDo);
+      const float scc = half_row_dot(sK, 16, half, sClsQ), dpcc = half_row_dot(sV, 16, half, sClsDo);
+      Pc = key < p.Lq ? exp2f(sc * sl2 - lse_c) : 0.f;
+      dSc = Pc * (dpc - delta_c) * p.scale;
+      Pcc = first ? exp2f(scc * sl2 - lse_c) : 0.f;
+      dScc = Pcc * (dpcc - delta_c) * p.scale;
+      // dQ_cls += sum_j dS_j k_j (this lane: columns 2 * lane, 2 * lane + 1); K stays intact until the end of the unit
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float dsj = __shfl_sync(0xffffffffu, dSc, j);
+        const float2 kk = ld_shared_bf16x2(sK + swz(j, lane >> 2) + (lane & 3) * 4);
+        dqc0 = fmaf(dsj, kk.x, dqc0);
+        dqc1 = fmaf(dsj, kk.y, dqc1);
+      }
+      {
+        const float2 kk = ld_shared_bf16x2(sK + swz(16, lane >> 2) + (lane & 3) * 4);
+        dqc0 = fmaf(dScc, kk.x, dqc0);
+        dqc1 = fmaf(dScc, kk.y, dqc1);
+      }
+    }
+    // rank-1 update of a gradient fragment (rows g, g + 8 = keys) with the CLS query's term: acc += w[key] * vec[col]
+    auto add_cls_term = [&](float (&a)[8][4], float (&ck)[8][2], float w, float wcc, uint32_t vec) {
+      const float w0 = __shfl_sync(0xffffffffu, w, g), w1 = __shfl_sync(0xffffffffu, w, g + 8);
+#pragma unroll
+      for (int dt = 0; dt < 8; ++dt) {
+        const float2 x = ld_shared_bf16x2(vec + (dt * 8 + 2 * t) * 2);
+        a[dt][0] = fmaf(w0, x.x, a[dt][0]);
+        a[dt][1] = fmaf(w0, x.y, a[dt][1]);
+        a[dt][2] = fmaf(w1, x.x, a[dt][2]);
+        a[dt][3] = fmaf(w1, x.y, a[dt][3]);
+        if (g == 0) {                  // the CLS key / value row lives in lanes 0-3
+          ck[dt][0] = fmaf(wcc, x.x, ck[dt][0]);
+          ck[dt][1] = fmaf(wcc, x.y, ck[dt][1]);
+        }
+      }
+    };
     float acc[8][4];
     // ---- dV = P^T dO  (keys are the M dimension; the CLS slot is row 0 of a second, otherwise empty, key tile)
     {
@@ -426,6 +581,7 @@ time_attn_bwd_kernel(const Params p) {
         }
       }
     }
+    if (p.dcls_q) add_cls_term(acc, clsv, Pc, Pcc, sClsDo);        // dV_j += P_cls[j] dO_cls
     stage_and_store(sV, acc, p.Lq, p.dqkv + 2 * p.D + cur.h * HD, p.ld_dqkv, cur.base_row, rs, lane);
     // ---- dK = dS^T Q
     {
@@ -447,6 +603,7 @@ time_attn_bwd_kernel(const Params p) {
         }
       }
     }
+    if (p.dcls_q) add_cls_term(acc, clsk, dSc, dScc, sClsQ);       // dK_j += dS_cls[j] q_cls
     stage_and_store(sdO, acc, p.Lq, p.dqkv + p.D + cur.h * HD, p.ld_dqkv, cur.base_row, rs, lane);
     // ---- dQ = dS K
     {
@@ -468,12 +625,42 @@ time_attn_bwd_kernel(const Params p) {
       }
     }
     stage_and_store(sQ, acc, p.Lq, p.dqkv + cur.h * HD, p.ld_dqkv, cur.base_row, rs, lane);
-    if (u + 1 == u1 || nxt.bh != cur.bh) flush_cls(cur);
+    if (u + 1 == u1 || nxt.bh != cur.bh) { flush_cls(cur); flush_dq(cur); }
     cur = nxt;
     __syncwarp();
   }
 }
 
+}  // namespace tattn
+
+namespace tattn {
+// CLS output row of a (clip, head) from its P partials (max, sum, o[64]): o = sum_j w_j o_j / sum_j w_j l_j
+__global__ void __launch_bounds__(64)
+time_cls_combine_kernel(const float* __restrict__ part, __nv_bfloat16* __restrict__ out, long long ld_out, float* __restrict__ lse,
+                        int H, int P, long long clip_rows, float scale) {
+  const int b = blockIdx.x / H, h = blockIdx.x - b * H, d = threadIdx.x;
+  const float* pp = part + ((long long)b * H + h) * P * 66;
+  float M = -INFINITY;
+  for (int j = 0; j < P; ++j) M = fmaxf(M, pp[(long long)j * 66]);
+  const float sl2 = scale * LOG2E;
+  float L = 0.f, o = 0.f;
+  for (int j = 0; j < P; ++j) {
+    const float w = exp2f((pp[(long long)j * 66] - M) * sl2);
+    L += w * pp[(long long)j * 66 + 1];
+    o += w * pp[(long long)j * 66 + 2 + d];
+  }
+  const long long row = (long long)b * clip_rows;
+  out[row * ld_out + h * HD + d] = __float2bfloat16_rn(o / L);
+  if (d == 0) lse[row * H + h] = M * scale + logf(L);
+}
+// dqkv[cls row] = bf16([dq_cls | dk_cls | dv_cls]) from the fp32 accumulators
+__global__ void time_cls_finalize_kernel(const float* __restrict__ dcls_kv, const float* __restrict__ dcls_q,
+                                         __nv_bfloat16* __restrict__ dqkv, long long lddq, int H, int D, long long N) {
+  const int b = blockIdx.x / H, h = blockIdx.x - b * H;
+  const int part = threadIdx.x >> 6, d = threadIdx.x & 63;
+  const float v = part == 0 ? dcls_q[((long long)b * H + h) * HD + d] : dcls_kv[(((long long)b * H + h) * 2 + (part - 1)) * HD + d];
+  dqkv[(long long)b * N * lddq + part * D + h * HD + d] = __float2bfloat16_rn(v);
+}
 }  // namespace tattn
 
 // ---- launchers (called from lv_group_attn_fwd / lv_group_attn_bwd for mode 1 with <= 16 frames)
@@ -491,12 +678,13 @@ static void fill(tattn::Params& p, int B, int H, int T, int n) {
   p.scale = 0.125f;
 }
 
-int time_attn_small_fwd(const void* qkv, long long ld_qkv, void* out, long long ld_out, float* lse, int B, int H, int T, int n,
-                        cudaStream_t st) {
+static int time_fwd_launch(const void* qkv, long long ld_qkv, void* out, long long ld_out, float* lse, float* cls_part, int B, int H,
+                           int T, int n, cudaStream_t st) {
   tattn::Params p{};
   fill(p, B, H, T, n);
   p.qkv = (const __nv_bfloat16*)qkv; p.ld_qkv = ld_qkv;
   p.out = (__nv_bfloat16*)out; p.ld_out = ld_out; p.lse = lse;
+  p.cls_part = cls_part;
   const int smem = p.hc * tattn::FWD_WARP_BYTES;
   static bool configured = false;
   if (!configured) {
@@ -507,14 +695,33 @@ int time_attn_small_fwd(const void* qkv, long long ld_qkv, void* out, long long 
   int grid = sm_count();
   if (grid > p.units) grid = p.units;
   tattn::time_attn_fwd_kernel<<<grid, p.hc * 32, smem, st>>>(p);
-  return check_launch("lv_group_attn_fwd(time)");
+  int rc = check_launch("lv_group_attn_fwd(time)");
+  if (rc || !cls_part) return rc;
+  tattn::time_cls_combine_kernel<<<B * H, 64, 0, st>>>(cls_part, (__nv_bfloat16*)out, ld_out, lse, H, n, p.clip_rows, p.scale);
+  return check_launch("lv_time_attn_fwd_cls(combine)");
 }
+
+int time_attn_small_fwd(const void* qkv, long long ld_qkv, void* out, long long ld_out, float* lse, int B, int H, int T, int n,
+                        cudaStream_t st) {
+  return time_fwd_launch(qkv, ld_qkv, out, ld_out, lse, nullptr, B, H, T, n, st);
+}
+
+static int time_bwd_launch(const void* qkv, long long ld_qkv, const void* out, long long ld_out, const float* lse, const void* dout,
+                           long long ld_dout, void* dqkv, long long ld_dqkv, float* dcls_kv, float* dcls_q, int B, int H, int T, int n,
+                           cudaStream_t st);
 
 int time_attn_small_bwd(const void* qkv, long long ld_qkv, const void* out, long long ld_out, const float* lse, const void* dout,
                         long long ld_dout, void* dqkv, long long ld_dqkv, float* dcls_kv, int B, int H, int T, int n,
                         cudaStream_t st) {
+  return time_bwd_launch(qkv, ld_qkv, out, ld_out, lse, dout, ld_dout, dqkv, ld_dqkv, dcls_kv, nullptr, B, H, T, n, st);
+}
+
+static int time_bwd_launch(const void* qkv, long long ld_qkv, const void* out, long long ld_out, const float* lse, const void* dout,
+                           long long ld_dout, void* dqkv, long long ld_dqkv, float* dcls_kv, float* dcls_q, int B, int H, int T, int n,
+                           cudaStream_t st) {
   tattn::Params p{};
   fill(p, B, H, T, n);
+  p.dcls_q = dcls_q;
   p.qkv = (const __nv_bfloat16*)qkv; p.ld_qkv = ld_qkv;
   p.out = (__nv_bfloat16*)out; p.ld_out = ld_out; p.lse = (float*)lse;
   p.dout = (const __nv_bfloat16*)dout; p.ld_dout = ld_dout;
@@ -529,7 +736,32 @@ int time_attn_small_bwd(const void* qkv, long long ld_qkv, const void* out, long
   int grid = sm_count();
   if (grid > p.units) grid = p.units;
   tattn::time_attn_bwd_kernel<<<grid, p.hc * 32, smem, st>>>(p);
-  return check_launch("lv_group_attn_bwd(time)");
+  int rc = check_launch("lv_group_attn_bwd(time)");
+  if (rc || !dcls_q) return rc;
+  tattn::time_cls_finalize_kernel<<<B * H, 192, 0, st>>>(dcls_kv, dcls_q, (__nv_bfloat16*)dqkv, ld_dqkv, H, p.D, p.clip_rows);
+  return check_launch("lv_time_attn_bwd_cls(finalize)");
 }
+
+}  // namespace lv
+
+// Time attention INCLUDING the CLS query row (pairs with lv_space_attn_*_tc_cls; <= 16 frames): fwd cls_part = fp32 scratch
+// [B*H*n*66]; bwd dcls_kv fp32 [B][H][2][64] and dcls_q fp32 [B][H][64] zeroed by the caller.  Every row of out / lse / dqkv is
+// written.  Replace lv_group_attn_fwd(mode 1) + lv_cls_attn_fwd and lv_group_attn_bwd(mode 1) + lv_cls_attn_bwd + lv_cls_kv_finalize.
+extern "C" int lv_time_attn_fwd_cls(const void* qkv, int64_t ld_qkv, void* out, int64_t ld_out, float* lse, float* cls_part, int B,
+                                    int H, int T, int n, void* stream) {
+  LV_REQUIRE(qkv && out && lse && cls_part && B > 0 && H > 0 && T > 0 && T <= 16 && n > 0, "lv_time_attn_fwd_cls: bad arguments (T <= 16)");
+  LV_REQUIRE(ld_qkv % 8 == 0 && ld_out % 8 == 0, "lv_time_attn_fwd_cls: leading dimensions must be multiples of 8");
+  return lv::time_fwd_launch(qkv, ld_qkv, out, ld_out, lse, cls_part, B, H, T, n, (cudaStream_t)stream);
+}
+extern "C" int lv_time_attn_bwd_cls(const void* qkv, int64_t ld_qkv, const void* out, int64_t ld_out, const float* lse,
+                                    const void* dout, int64_t ld_dout, void* dqkv, int64_t ld_dqkv, float* dcls_kv, float* dcls_q,
+                                    int B, int H, int T, int n, void* stream) {
+  LV_REQUIRE(qkv && out && lse && dout && dqkv && dcls_kv && dcls_q && B > 0 && H > 0 && T > 0 && T <= 16 && n > 0,
+             "lv_time_attn_bwd_cls: bad arguments (T <= 16)");
+  LV_REQUIRE(ld_qkv % 8 == 0 && ld_out % 8 == 0 && ld_dout % 8 == 0 && ld_dqkv % 8 == 0, "lv_time_attn_bwd_cls: leading dimensions must be multiples of 8");
+  return lv::time_bwd_launch(qkv, ld_qkv, out, ld_out, lse, dout, ld_dout, dqkv, ld_dqkv, dcls_kv, dcls_q, B, H, T, n, (cudaStream_t)stream);
+}
+
+namespace lv {
 
 }  // namespace lv

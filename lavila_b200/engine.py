@@ -170,6 +170,8 @@ def attn_sub_fwd(x_ln, resid, P, dims, mode, eps, gate=None):
         ops.group_attn_fwd(qkv, att, lse, mode, B, H, Lctx=dims["L"])
     elif mode == MODE_SPACE and ops.space_attn_cls_fused_supported(dims["n"]):
         ops.space_attn_fwd_cls(qkv, att, lse, B, H, dims["T"], dims["n"])        # CLS query inside the tcgen05 group kernel
+    elif mode == MODE_TIME and ops.time_attn_cls_fused_supported(dims["T"]):
+        ops.time_attn_fwd_cls(qkv, att, lse, B, H, dims["T"], dims["n"])         # CLS query next to every (clip, position) unit
     else:
         ops.group_attn_fwd(qkv, att, lse, mode, B, H, T=dims["T"], n=dims["n"])
         ops.cls_attn_fwd(qkv, att, lse, B, H, dims["N"])
@@ -214,6 +216,8 @@ def attn_sub_bwd(dy, dy_b, P, S, adds=(), want_bf16=True):
         ops.group_attn_bwd(S["qkv"], S["att"], S["lse"], datt, dqkv, None, 0, mode, B, H, Lctx=dims["L"])
     elif mode == MODE_SPACE and ops.space_attn_cls_fused_supported(dims["n"]):
         ops.space_attn_bwd_cls(S["qkv"], S["att"], S["lse"], datt, dqkv, B, H, dims["T"], dims["n"])
+    elif mode == MODE_TIME and ops.time_attn_cls_fused_supported(dims["T"]):
+        ops.time_attn_bwd_cls(S["qkv"], S["att"], S["lse"], datt, dqkv, B, H, dims["T"], dims["n"])
     else:
         # group kernel first (plain stores), then the streaming CLS-query kernel accumulates on top: keeps the
         # read-modify-write latency out of the tensor-core kernel's critical path
@@ -753,6 +757,8 @@ class VarAttentionFn(torch.autograd.Function):
         lse = torch.empty(M, heads, device=dev, dtype=F32)
         if mode == MODE_SPACE and ops.space_attn_cls_fused_supported(patches):
             ops.space_attn_fwd_cls(qkv, att, lse, B, heads, frames, patches)
+        elif mode == MODE_TIME and ops.time_attn_cls_fused_supported(frames):
+            ops.time_attn_fwd_cls(qkv, att, lse, B, heads, frames, patches)
         else:
             ops.group_attn_fwd(qkv, att, lse, mode, B, heads, T=frames, n=patches)
             ops.cls_attn_fwd(qkv, att, lse, B, heads, N)
@@ -778,6 +784,8 @@ class VarAttentionFn(torch.autograd.Function):
         dqkv = torch.empty(M, 3 * D, device=dev, dtype=BF16)
         if mode == MODE_SPACE and ops.space_attn_cls_fused_supported(patches):
             ops.space_attn_bwd_cls(qkv, att, lse, datt, dqkv, B, heads, frames, patches)
+        elif mode == MODE_TIME and ops.time_attn_cls_fused_supported(frames):
+            ops.time_attn_bwd_cls(qkv, att, lse, datt, dqkv, B, heads, frames, patches)
         else:
             dcls = torch.zeros(B, heads, 2, 64, device=dev, dtype=F32)
             ops.group_attn_bwd(qkv, att, lse, datt, dqkv, dcls, 0, mode, B, heads, T=frames, n=patches)

@@ -177,6 +177,28 @@ def space_attn_bwd_cls(qkv, out, lse, dout, dqkv, B, H, T, n):
     L.check(rc, "lv_space_attn_bwd_tc_cls")
 
 
+def time_attn_cls_fused_supported(T):
+    return USE_TC_CLS_FUSION and 0 < T <= 16
+
+
+def time_attn_fwd_cls(qkv, out, lse, B, H, T, n):
+    """Time attention forward for every row, CLS rows included (lv_time_attn_fwd_cls)."""
+    part = torch.empty(B * H * n * 66, device=qkv.device, dtype=F32)
+    rc = L.lib().lv_time_attn_fwd_cls(qkv.data_ptr(), qkv.stride(0), out.data_ptr(), out.stride(0), lse.data_ptr(),
+                                      part.data_ptr(), B, H, T, n, _stream())
+    L.check(rc, "lv_time_attn_fwd_cls")
+
+
+def time_attn_bwd_cls(qkv, out, lse, dout, dqkv, B, H, T, n):
+    """Time attention backward for every row, CLS rows included (lv_time_attn_bwd_cls)."""
+    scratch = torch.zeros(B * H * 3 * 64, device=qkv.device, dtype=F32)
+    dkv, dq = scratch[:B * H * 128], scratch[B * H * 128:]
+    rc = L.lib().lv_time_attn_bwd_cls(qkv.data_ptr(), qkv.stride(0), out.data_ptr(), out.stride(0), lse.data_ptr(),
+                                      dout.data_ptr(), dout.stride(0), dqkv.data_ptr(), dqkv.stride(0), dkv.data_ptr(),
+                                      dq.data_ptr(), B, H, T, n, _stream())
+    L.check(rc, "lv_time_attn_bwd_cls")
+
+
 def flash_attn_fwd(q, k, v, out, B, H, Lq, Lk, *, q_rows, kv_rows, ld_q, ld_kv, ld_out, kv_head_stride=64, causal=False,
                    scale=0.125):
     rc = L.lib().lv_flash_attn_fwd(q.data_ptr(), ld_q, q_rows, k.data_ptr(), v.data_ptr(), ld_kv, kv_rows, kv_head_stride,

@@ -424,7 +424,8 @@ DOUBLES = ("gemm", "wgrad_splits", "layernorm_fwd", "layernorm_bwd", "group_attn
            "patch_im2col", "embed_assemble", "embed_assemble_bwd", "text_embed", "text_embed_bwd", "argmax_i64", "gather_rows",
            "l2norm_fwd", "l2norm_bwd", "clip_loss_fwd", "clip_loss_bwd", "flash_attn_fwd", "flash_attn_fwd_dyn", "gemm_skinny",
            "ssl_clip_loss_fwd", "ssl_clip_loss_bwd", "top_p_filter_",
-           "space_attn_cls_fused_supported", "space_attn_fwd_cls", "space_attn_bwd_cls")
+           "space_attn_cls_fused_supported", "space_attn_fwd_cls", "space_attn_bwd_cls",
+           "time_attn_cls_fused_supported", "time_attn_fwd_cls", "time_attn_bwd_cls")
 
 
 def top_p_filter_(logits, temperature, top_p):
@@ -450,6 +451,22 @@ def space_attn_fwd_cls(qkv, out, lse, B, H, T, n):
 def space_attn_bwd_cls(qkv, out, lse, dout, dqkv, B, H, T, n):
     dcls = torch.zeros(B, H, 2, 64)
     group_attn_bwd(qkv, out, lse, dout, dqkv, dcls, 0, 0, B, H, T=T, n=n)
+    cls_attn_bwd(qkv, out, dout, lse, dqkv, dcls, B, H, 1 + T * n, accumulate=True)
+    cls_kv_finalize(dcls, dqkv, B, H, 1 + T * n)
+
+
+def time_attn_cls_fused_supported(T):
+    return 0 < T <= 16
+
+
+def time_attn_fwd_cls(qkv, out, lse, B, H, T, n):
+    group_attn_fwd(qkv, out, lse, 1, B, H, T=T, n=n)
+    cls_attn_fwd(qkv, out, lse, B, H, 1 + T * n)
+
+
+def time_attn_bwd_cls(qkv, out, lse, dout, dqkv, B, H, T, n):
+    dcls = torch.zeros(B, H, 2, 64)
+    group_attn_bwd(qkv, out, lse, dout, dqkv, dcls, 0, 1, B, H, T=T, n=n)
     cls_attn_bwd(qkv, out, dout, lse, dqkv, dcls, B, H, 1 + T * n, accumulate=True)
     cls_kv_finalize(dcls, dqkv, B, H, 1 + T * n)
 

@@ -5,6 +5,7 @@ sys.path.insert(0, ".")
 from lavila_b200 import ops
 
 B, H, T, n = (int(x) for x in sys.argv[1:5]) if len(sys.argv) > 4 else (4, 12, 16, 196)
+MODE = int(sys.argv[5]) if len(sys.argv) > 5 else 0       # 0 = space, 1 = time
 D = 64 * H
 N = 1 + T * n
 M = B * N
@@ -22,7 +23,7 @@ def rel(a, b):
 def ref_fwd():
     out = torch.zeros(M, D, device=dev, dtype=torch.bfloat16)
     lse = torch.zeros(M, H, device=dev)
-    ops.group_attn_fwd(qkv, out, lse, 0, B, H, T=T, n=n)
+    ops.group_attn_fwd(qkv, out, lse, MODE, B, H, T=T, n=n)
     ops.cls_attn_fwd(qkv, out, lse, B, H, N)
     return out, lse
 
@@ -30,14 +31,14 @@ def ref_fwd():
 def fused_fwd():
     out = torch.zeros(M, D, device=dev, dtype=torch.bfloat16)
     lse = torch.zeros(M, H, device=dev)
-    ops.space_attn_fwd_cls(qkv, out, lse, B, H, T, n)
+    (ops.time_attn_fwd_cls if MODE else ops.space_attn_fwd_cls)(qkv, out, lse, B, H, T, n)
     return out, lse
 
 
 def ref_bwd(o, l):
     dqkv = torch.full((M, 3 * D), 7.0, device=dev, dtype=torch.bfloat16)
     dcls = torch.zeros(B, H, 2, 64, device=dev)
-    ops.group_attn_bwd(qkv, o, l, dout, dqkv, dcls, 0, 0, B, H, T=T, n=n)
+    ops.group_attn_bwd(qkv, o, l, dout, dqkv, dcls, 0, MODE, B, H, T=T, n=n)
     ops.cls_attn_bwd(qkv, o, dout, l, dqkv, dcls, B, H, N, accumulate=True)
     ops.cls_kv_finalize(dcls, dqkv, B, H, N)
     return dqkv
@@ -45,7 +46,7 @@ def ref_bwd(o, l):
 
 def fused_bwd(o, l):
     dqkv = torch.full((M, 3 * D), 7.0, device=dev, dtype=torch.bfloat16)
-    ops.space_attn_bwd_cls(qkv, o, l, dout, dqkv, B, H, T, n)
+    (ops.time_attn_bwd_cls if MODE else ops.space_attn_bwd_cls)(qkv, o, l, dout, dqkv, B, H, T, n)
     return dqkv
 
 

@@ -1,0 +1,13 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 120 python tools/gpu_cls_fusion_probe.py 2 2 4 9 1 2>&1 | tail -10
+timeout 120 python tools/gpu_cls_fusion_probe.py 3 12 16 196 1 2>&1 | tail -10
+timeout 120 python tools/gpu_cls_fusion_probe.py 64 12 16 196 1 2>&1 | tail -10
+( timeout 600 python -m pytest tests -m gpu -q -x -p no:cacheprovider ) > gpurun_out/r02_c20_pytest.log 2>&1; echo "pytest rc=$?"; tail -4 gpurun_out/r02_c20_pytest.log | cut -c1-300
+for v in 1 0; do
+LAVILA_B200_CLS_FUSION=$v timeout 400 python bench.py --steps 10 --warmup 3 --no-eager-baseline --no-cpu-baseline --no-narrator --no-e2e > gpurun_out/r02_c20_bench_$v.json 2> gpurun_out/r02_c20_bench.err; python - <<PY
+import json
+d=json.loads(open('gpurun_out/r02_c20_bench_$v.json').read())
+print("fusion=$v", {k:d[k] for k in ('value','ms_per_step')}, d['block_roofline']['frac'], d['block_roofline']['ms'], d['roofline']['frac'], d['roofline']['gemm_ms_per_step'], d['clocks']['sm_mhz'])
+PY
+done
