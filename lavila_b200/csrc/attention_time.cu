@@ -297,7 +297,7 @@ time_attn_fwd_kernel(const Params p) {
       const int key = lane & 15, half = lane >> 4;
       const bool first = (c.base_row - c.cls_row) == 1;                   // spatial position 0: this unit also owns the CLS key
       float sc = half_row_dot(sK, key, half, sCls);
-      const float scc = half_row_dot(sK, 16, half, sCls);                 // q_cls . k_cls
+      const float scc = first ? half_row_dot(sK, 16, half, sCls) : 0.f;   // q_cls . k_cls (warp-uniform branch)
       sc = key < p.Lq ? sc : -INFINITY;
       float mc = warp_max16(sc);
       if (first) mc = fmaxf(mc, scc);
@@ -525,7 +525,8 @@ time_attn_bwd_kernel(const Params p) {
       const int key = lane & 15, half = lane >> 4;
       const bool first = (cur.base_row - cur.cls_row) == 1;
       const float sc = half_row_dot(sK, key, half, sClsQ), dpc = half_row_dot(sV, key, half, sClsDo);
-      const float scc = half_row_dot(sK, 16, half, sClsQ), dpcc = half_row_dot(sV, 16, half, sClsDo);
+      const float scc = first ? half_row_dot(sK, 16, half, sClsQ) : 0.f;          // the CLS key pairs with the CLS query once per
+      const float dpcc = first ? half_row_dot(sV, 16, half, sClsDo) : 0.f;        // clip: in the unit of position 0 (warp-uniform)
       Pc = key < p.Lq ? exp2f(sc * sl2 - lse_c) : 0.f;
       dSc = Pc * (dpc - delta_c) * p.scale;
       Pcc = first ? exp2f(scc * sl2 - lse_c) : 0.f;

@@ -44,16 +44,21 @@ constexpr int TMEM_COLS = 512;
 //   0  transposing epilogue of gemm_epilogue.cuh (per-thread global loads / stores; every flag set), 6 operand stages
 //   1  row-per-thread epilogue with TMA stores (gemm_epilogue_rows.cuh), output-only flag sets, 5 stages + 32 KB staging
 //   2  the same + TMA prefetch of the saved pre-activation slab (dQuickGELU), 4 stages + 32 KB staging + 64 KB slabs
+//   3  fp32 output + fp32 residual (proj / fc2 forward): residual boxes in by TMA, added in place, out by TMA; 4 stages + 64 KB
 __host__ __device__ constexpr int stages_of(int mode) { return mode == 0 ? 6 : (mode == 1 ? 5 : 4); }
 __host__ __device__ constexpr int epi_bytes_of(int mode) {
   return mode == 0 ? EPI_WARPS * 32 * EPI_PITCH * 4
+       : mode == 3 ? EPI_WARPS * gemm::ROWS_F32_BYTES
                    : EPI_WARPS * (gemm::ROWS_STAGE_BYTES + (mode == 2 ? gemm::ROWS_AUX_BYTES : 0));
 }
-__host__ __device__ constexpr int num_bars_of(int mode) { return 2 * stages_of(mode) + 4 + (mode == 2 ? EPI_WARPS : 0); }
+__host__ __device__ constexpr int num_bars_of(int mode) {
+  return 2 * stages_of(mode) + 4 + (mode == 2 ? EPI_WARPS : 0) + (mode == 3 ? 2 * EPI_WARPS : 0);
+}
 __host__ __device__ constexpr int smem_bytes_of(int mode) {
   return 1024 + stages_of(mode) * STAGE_BYTES + epi_bytes_of(mode) + num_bars_of(mode) * 8 + 16;
 }
-static_assert(smem_bytes_of(0) <= 227 * 1024 && smem_bytes_of(1) <= 227 * 1024 && smem_bytes_of(2) <= 227 * 1024, "shared memory budget");
+static_assert(smem_bytes_of(0) <= 227 * 1024 && smem_bytes_of(1) <= 227 * 1024 && smem_bytes_of(2) <= 227 * 1024 &&
+              smem_bytes_of(3) <= 227 * 1024, "shared memory budget");
 constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -141,6 +146,10 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (MODE == 2) {
       prefetch_tmap(&tmAux);
       for (int w = 0; w < EPI_WARPS; ++w) mbar_init(&aux_bar[w], 1);
+    }
+    if (MODE == 3) {
+      prefetch_tmap(&tmAux);     // the residual's tensor map travels in the aux slot
+      for (int w = 0; w < 2 * EPI_WARPS; ++w) mbar_init(&aux_bar[w], 1);
     }
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
@@ -256,6 +265,25 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         __syncwarp();
         if (lane == 0) mbar_arrive_remote(&tempty_bar[as], 0);   // the leader's MMA warp owns the accumulator hand-off
       }
+    } else if constexpr (MODE == 3) {
+      uint8_t* stage = sEpiRaw + e * gemm::ROWS_F32_BYTES;
+      uint32_t ph[2] = {0u, 0u};
+      float scale = 1.0f;
+      if (flags & LV_EPI_SCALE) {
+        scale = __ldg(g.scale_ptr);
+        if (flags & LV_EPI_SCALE_TANH) scale = tanhf(scale);
+      }
+      for (int it = 0; iter.next(tile, kb0, kb1); ++it) {
+        const int m_blk = tile / g.num_n_blks;
+        const int n_blk = tile - m_blk * g.num_n_blks;
+        const int as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        uint64_t* tempty = &tempty_bar[as];
+        gemm::epilogue_rows_f32_tile<CT_FLAGS>(g, scale, stage, &aux_bar[2 * e], ph, &tmO, &tmAux, &tfull_bar[as], aphase,
+                                               tmem_base + as * BN, m_blk * 256 + (int)rank * BM_CTA + q * 32, n_blk * BN, half, q,
+                                               lane, [&]() { if (lane == 0) mbar_arrive_remote(tempty, 0); });
+      }
+      if (lane == 0) tma_store_wait_all();
     } else {
       uint8_t* stage = sEpiRaw + e * gemm::ROWS_STAGE_BYTES;
       uint8_t* aux = sEpiRaw + EPI_WARPS * gemm::ROWS_STAGE_BYTES + e * gemm::ROWS_AUX_BYTES;
@@ -331,6 +359,9 @@ static int try_spec(bool& hit, const Maps& tm, const Args& g, int rows_mode, cud
         constexpr int MODE = gemm::rows_needs_aux(F) ? 2 : 1;
         if (rows_mode == MODE) return launch<A_MN, B_MN, F, MODE>(tm, g, st);
       }
+      if constexpr (gemm::rows_f32_resid(F) && !A_MN && !B_MN) {
+        if (rows_mode == 3) return launch<A_MN, B_MN, F, 3>(tm, g, st);
+      }
       return launch<A_MN, B_MN, F, 0>(tm, g, st);
     }
   }
@@ -398,6 +429,12 @@ extern "C" int lv_gemm_bf16_2cta(const void* A, int64_t lda, int a_mn, const voi
     rc = make_tmap_2d(&tm.O, epi->out, 2, (uint64_t)N, (uint64_t)M, (uint64_t)epi->ldo, 32, 32, 64);
     if (!rc && (flags & LV_EPI_QUICKGELU)) rc = make_tmap_2d(&tm.O2, epi->out2, 2, (uint64_t)N, (uint64_t)M, (uint64_t)epi->ldo2, 32, 32, 64);
     if (!rc && (flags & LV_EPI_DQUICKGELU)) rc = make_tmap_2d(&tm.Aux, epi->aux, 2, (uint64_t)N, (uint64_t)M, (uint64_t)epi->ldaux, 32, 32, 64);
+    if (rc) return rc;
+  } else if (rows_epilogue_enabled() && !a_mn && !b_mn && gemm::rows_f32_resid(flags) && (reinterpret_cast<uintptr_t>(epi->out) & 15) == 0 &&
+             (epi->ldo & 3) == 0 && (reinterpret_cast<uintptr_t>(epi->resid) & 15) == 0 && (epi->ldr & 3) == 0) {
+    rows_mode = 3;
+    rc = make_tmap_2d(&tm.O, epi->out, 4, (uint64_t)N, (uint64_t)M, (uint64_t)epi->ldo, 32, 32, 128);
+    if (!rc) rc = make_tmap_2d(&tm.Aux, epi->resid, 4, (uint64_t)N, (uint64_t)M, (uint64_t)epi->ldr, 32, 32, 128);
     if (rc) return rc;
   }
 

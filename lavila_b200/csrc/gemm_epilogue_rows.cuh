@@ -39,6 +39,12 @@ __host__ __device__ constexpr bool rows_supported(int f) {
   return f == 0 || f == LV_EPI_BIAS || f == (LV_EPI_BIAS | LV_EPI_QUICKGELU) || f == LV_EPI_DQUICKGELU;
 }
 __host__ __device__ constexpr bool rows_needs_aux(int f) { return (f & LV_EPI_DQUICKGELU) != 0; }
+// fp32 output + fp32 residual (proj / fc2 forward: y = x + [tanh(gate) *] (a W^T + b), timesformer.py:181-196): mode 3
+__host__ __device__ constexpr bool rows_f32_resid(int f) {
+  return f == (LV_EPI_BIAS | LV_EPI_RESID | LV_EPI_OUT_F32) ||
+         f == (LV_EPI_BIAS | LV_EPI_SCALE | LV_EPI_SCALE_TANH | LV_EPI_RESID | LV_EPI_OUT_F32);
+}
+constexpr int ROWS_F32_BYTES = 8192;     // per warp: 2 x [32 rows x 32 fp32] (128B swizzle): residual box in, result box out, in place
 
 // One tile.  stage: this warp's 4 KB staging tile (1024-byte aligned).  aux: this warp's 8 KB slab of the saved pre-activation
 // (already requested; aux_bar completes when it has landed).  release(): hands the TMEM accumulator stage back.
@@ -138,6 +144,78 @@ __device__ __forceinline__ void epilogue_rows_tile(const Args& g, uint8_t* stage
     if (lane == 0) {
       tma_store_2d(tmO, stage + hsel * 2048, n, m_base);
       if (TWO_OUT) tma_store_2d(tmO2, stage + 2048, n, m_base);
+      tma_store_commit();
+    }
+  }
+}
+
+// fp32 output with an fp32 residual operand.  Per 32-column chunk the residual box [32 rows x 32 fp32] is fetched by TMA into one
+// of two per-warp 4 KB buffers (the next chunk's box is requested before the current one is processed), every thread adds its
+// accumulator row IN PLACE (8 conflict-free ld.shared.v4 / st.shared.v4 on the 128B-swizzled tile) and the same buffer is
+// handed to a TMA store.  No per-thread global loads or stores: the transposing epilogue needed 8 + 8 of them per thread and
+// chunk, each touching 8 rows x 64 bytes.  bars: two mbarriers of this warp (one per buffer); ph: their parities (kept by
+// the caller across tiles).
+template <int FLAGS, class Release>
+__device__ __forceinline__ void epilogue_rows_f32_tile(const Args& g, const float scale, uint8_t* stage, uint64_t* bars, uint32_t (&ph)[2],
+                                                       const CUtensorMap* tmO, const CUtensorMap* tmR, uint64_t* tfull,
+                                                       const uint32_t aphase, const uint32_t tmem_acc, const int m_base, const int n0,
+                                                       const int half, const int q, const int lane, Release release) {
+  constexpr int CPW = BN / 64;
+  const uint32_t st = smem_u32(stage);
+  const uint32_t trow = tmem_acc + (uint32_t(q * 32) << 16);
+  const int nbase = n0 + half * CPW * 32;
+  auto request = [&](int cc) {          // lane 0: residual box of chunk cc -> buffer cc & 1
+    mbar_arrive_expect_tx(&bars[cc & 1], 4096);
+    tma_load_2d(stage + (cc & 1) * 4096, tmR, &bars[cc & 1], nbase + cc * 32, m_base);
+  };
+  if (nbase < g.N && lane == 0) {
+    tma_store_wait_read_n<1>();         // buffer 0 was last read by the store of chunk 2 of the previous tile
+    request(0);
+  }
+  mbar_wait(tfull, aphase);
+  tc_fence_after();
+  uint32_t r[2][32];
+  if (nbase < g.N) tmem_ld_32x32(trow + half * CPW * 32, r[0]);
+#pragma unroll
+  for (int cc = 0; cc < CPW; ++cc) {
+    const int n = nbase + cc * 32;
+    const bool chunk_ok = n < g.N;
+    const bool next_ok = (cc + 1 < CPW) && (n + 32 < g.N);
+    if (chunk_ok) tmem_ld_wait();
+    uint32_t (&cur)[32] = r[cc & 1];
+    if (next_ok) tmem_ld_32x32(trow + (half * CPW + cc + 1) * 32, r[(cc + 1) & 1]);
+    if (!next_ok && chunk_ok) {
+      tc_fence_before();
+      __syncwarp();
+      release();
+    }
+    if (!chunk_ok) {
+      if (cc == 0) { tc_fence_before(); __syncwarp(); release(); }
+      break;
+    }
+    if (next_ok && lane == 0) {
+      tma_store_wait_read_n<0>();       // the other buffer: its store (chunk cc - 1) must have been read before it is refilled
+      request(cc + 1);
+    }
+    mbar_wait(&bars[cc & 1], ph[cc & 1]);
+    ph[cc & 1] ^= 1u;
+    const uint32_t buf = st + (cc & 1) * 4096;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const uint32_t addr = buf + sw128_off(lane, k);
+      const uint4 rr = ld_shared_v4u(addr);
+      float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+      if ((FLAGS & LV_EPI_BIAS) && n + 4 * k < g.N) b = __ldg(reinterpret_cast<const float4*>(g.bias + n) + k);
+      float v0 = __uint_as_float(cur[4 * k]) + b.x, v1 = __uint_as_float(cur[4 * k + 1]) + b.y;
+      float v2 = __uint_as_float(cur[4 * k + 2]) + b.z, v3 = __uint_as_float(cur[4 * k + 3]) + b.w;
+      if (FLAGS & LV_EPI_SCALE) { v0 *= scale; v1 *= scale; v2 *= scale; v3 *= scale; }
+      v0 += __uint_as_float(rr.x); v1 += __uint_as_float(rr.y); v2 += __uint_as_float(rr.z); v3 += __uint_as_float(rr.w);
+      st_shared_v4u(addr, __float_as_uint(v0), __float_as_uint(v1), __float_as_uint(v2), __float_as_uint(v3));
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      tma_store_2d(tmO, stage + (cc & 1) * 4096, n, m_base);
       tma_store_commit();
     }
   }
