@@ -430,7 +430,8 @@ extern "C" int lv_gemm_bf16_2cta(const void* A, int64_t lda, int a_mn, const voi
     if (!rc && (flags & LV_EPI_QUICKGELU)) rc = make_tmap_2d(&tm.O2, epi->out2, 2, (uint64_t)N, (uint64_t)M, (uint64_t)epi->ldo2, 32, 32, 64);
     if (!rc && (flags & LV_EPI_DQUICKGELU)) rc = make_tmap_2d(&tm.Aux, epi->aux, 2, (uint64_t)N, (uint64_t)M, (uint64_t)epi->ldaux, 32, 32, 64);
     if (rc) return rc;
-  } else if (rows_epilogue_enabled() && !a_mn && !b_mn && gemm::rows_f32_resid(flags) && (reinterpret_cast<uintptr_t>(epi->out) & 15) == 0 &&
+  } else if (rows_epilogue_enabled() && !a_mn && !b_mn && gemm::rows_f32_resid(flags) && K < 2048 &&   // deep K keeps 6 operand stages
+             (reinterpret_cast<uintptr_t>(epi->out) & 15) == 0 &&
              (epi->ldo & 3) == 0 && (reinterpret_cast<uintptr_t>(epi->resid) & 15) == 0 && (epi->ldr & 3) == 0) {
     rows_mode = 3;
     rc = make_tmap_2d(&tm.O, epi->out, 4, (uint64_t)N, (uint64_t)M, (uint64_t)epi->ldo, 32, 32, 128);
