@@ -24,12 +24,13 @@ ATT_F = GROUPS * 2 * 2 * (n + 1) * n * 64    # QK^T + PV, MAC = 2
 def model():
     """kernel-name regex -> (bound, algorithmic bytes, algorithmic flops, what)."""
     return [
-        (r"space_attn_fwd_tc", ("tensor+SFU", 4 * u, ATT_F, "q,k,v read + o written; 2 GEMMs of 196 x 197 x 64 per group")),
+        (r"space_attn_fwd_tc", ("tensor+SFU", 4 * u, ATT_F, "q,k,v read + o written; 2 GEMMs of 196 x 197 x 64 per group (round 2: + the fused CLS query row)")),
         (r"space_attn_bwd_tc", ("tensor+SFU", 8 * u, 2.5 * ATT_F, "q,k,v,o,do read + dq,dk,dv written; 5 GEMMs per group")),
-        (r"time_attn_fwd", ("hbm", 4 * u, 0, "q,k,v read + o written (17 keys per group)")),
+        (r"time_attn_fwd", ("hbm", 4 * u, 0, "q,k,v read + o written (17 keys per group; round 2: + the fused CLS query partials)")),
         (r"time_attn_bwd", ("hbm", 8 * u, 0, "q,k,v,o,do read + dq,dk,dv written")),
         (r"cls_attn_fwd", ("hbm", 2 * u, 0, "k,v of every token read once")),
         (r"cls_attn_bwd", ("hbm", 6 * u, 0, "k,v read; dk,dv read-modify-written")),
+
         (r"ln_fwd_kernel", ("hbm", 3 * u, 0, "fp32 x read, bf16 y written")),
         (r"ln_bwd_kernel<6, 1, 2, 1>", ("hbm", 10 * u, 0, "bf16 dy + fp32 x + 2 fp32 adds read, fp32 + bf16 dx written")),
         (r"ln_bwd_kernel<6, 2, 1, 1>", ("hbm", 8 * u, 0, "bf16 dy + fp32 x + 1 fp32 add read, fp32 + bf16 dx written")),
