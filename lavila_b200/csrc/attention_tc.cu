@@ -12,6 +12,7 @@
 // Numerics: bf16 operands, fp32 accumulation and softmax -- same contract as the mma.sync kernels in attention.cu,
 // which remain in use for the HBM-bound time attention (17 keys) and the small text tower.
 #include <mutex>
+#include <type_traits>
 
 #include "../../include/lavila_b200.h"
 #include "host_common.h"
@@ -648,17 +649,30 @@ space_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __gri
           mbar_wait(bar_pds, step & 1);
           LV_STAMP(3 + step * 4);
           tc_fence_after();
-          const int nq_steps = qt ? 5 : 8;       // 80 or 128 query columns
-          for (int s2 = 0; s2 < nq_steps; ++s2) {
-            const uint32_t a_off = (s2 >> 2) * 16384 + (s2 & 3) * 32;
-            const uint32_t b_off = (qt * 128 + s2 * 16) * 128;
-            tc_mma_bf16(tmem_base + TB_DV, dk(pt_base + a_off), dmn(do_base + b_off, 8192), idesc_kv, (qt > 0 || s2 > 0));
-            tc_mma_bf16(tmem_base + TB_DK, dk(ds_base + a_off), dmn(q_base + b_off, 8192), idesc_kv, (qt > 0 || s2 > 0));
-          }
-          const int nk_steps = kt ? 5 : 8;       // keys 128..207 or 0..127
-          for (int s2 = 0; s2 < nk_steps; ++s2)
-            tc_mma_bf16(tmem_base + TB_DQ + qt * 64, dmn(ds_base + s2 * 2048, 16384), dmn(k_base + (kt * 128 + s2 * 16) * 128, 8192),
-                        idesc_dq, (kt > 0 || s2 > 0));
+          // The MMA-issuing thread is on the critical path (one thread, ~110 tcgen05.mma per group): trip counts are compile-time
+          // (5 or 8 k-steps of 16) and every descriptor is the first one of its tile plus an immediate (the 14-bit address field
+          // counts 16-byte units and never carries here), so an MMA costs an add and the issue itself.
+          const uint64_t d_pt = dk(pt_base), d_ds = dk(ds_base);
+          const uint64_t d_do = dmn(do_base + qt * 128 * 128, 8192), d_q = dmn(q_base + qt * 128 * 128, 8192);
+          const uint64_t d_dst = dmn(ds_base, 16384), d_k = dmn(k_base + kt * 128 * 128, 8192);
+          const uint32_t acc0 = qt > 0 ? 1u : 0u, accq = kt > 0 ? 1u : 0u;
+          auto issue_kv = [&](auto nsteps) {
+#pragma unroll
+            for (int s2 = 0; s2 < decltype(nsteps)::value; ++s2) {
+              const uint64_t a_off = (uint64_t)(((s2 >> 2) * 16384 + (s2 & 3) * 32) >> 4);
+              const uint64_t b_off = (uint64_t)((s2 * 16 * 128) >> 4);
+              tc_mma_bf16(tmem_base + TB_DV, d_pt + a_off, d_do + b_off, idesc_kv, s2 > 0 ? 1u : acc0);
+              tc_mma_bf16(tmem_base + TB_DK, d_ds + a_off, d_q + b_off, idesc_kv, s2 > 0 ? 1u : acc0);
+            }
+          };
+          auto issue_dq = [&](auto nsteps) {
+#pragma unroll
+            for (int s2 = 0; s2 < decltype(nsteps)::value; ++s2)
+              tc_mma_bf16(tmem_base + TB_DQ + qt * 64, d_dst + (uint64_t)((s2 * 2048) >> 4), d_k + (uint64_t)((s2 * 16 * 128) >> 4),
+                          idesc_dq, s2 > 0 ? 1u : accq);
+          };
+          if (qt) issue_kv(std::integral_constant<int, 5>{}); else issue_kv(std::integral_constant<int, 8>{});   // 80 / 128 query columns
+          if (kt) issue_dq(std::integral_constant<int, 5>{}); else issue_dq(std::integral_constant<int, 8>{});   // keys 128..207 / 0..127
           tc_commit(bar_mma3);
           // the next step's S^T / dP^T MMAs queue right behind: the elementwise warps find them ready as soon as the
           // staged tiles of this step have been consumed
