@@ -301,7 +301,7 @@ def run_ours(args):
         ddp_exposed = {"ms_per_step_sync": round(ms_sync / k, 3), "ms_per_step_no_sync": round(float(t.item()) / k, 3),
                        "ddp_allreduce_exposed_ms": round((ms_sync - float(t.item())) / k, 3), "steps": k}
 
-    narr = None
+    narr = inp = None
     if rank == 0 and world == 1 and not args.no_narrator and args.model == "base":
         # free the dual-encoder first: the narrator (TSF-L/14 + GPT-2 XL, 1.9 B parameters) is measured on an empty device
         peak_mem_gb = round(torch.cuda.max_memory_allocated() / 2 ** 30, 1)
@@ -314,6 +314,10 @@ def run_ours(args):
             narr = narrator_leg(dev)
         except Exception as e:          # the headline metric must not be lost to the secondary leg
             narr = {"error": repr(e)[:300]}
+        try:
+            inp = input_pipeline_leg(dev)
+        except Exception as e:
+            inp = {"error": repr(e)[:300]}
     else:
         peak_mem_gb = round(torch.cuda.max_memory_allocated() / 2 ** 30, 1)
 
@@ -343,6 +347,8 @@ def run_ours(args):
         }
         if narr is not None:
             line["narrator"] = narr
+        if inp is not None:
+            line["input_pipeline"] = inp
         if eager and eager.get("value"):
             line["vs_eager"] = {"device_timed": round(value / eager["value"], 3),
                                 "e2e": round(e2e["value"] / eager["value"], 3) if e2e else None,
@@ -463,6 +469,89 @@ def narrator_leg(dev, batch=32, frames=4, max_len=77):
     del model
     torch.cuda.empty_cache()
     return out
+
+
+def input_pipeline_leg(dev, batch=64, frames=16, src_hw=(288, 384), crop=224, cpu_budget_s=8.0):
+    """the train transform of main_pretrain.py:263-272 for one batch of BASELINE config 2 (64 clips x 16 decoded
+    uint8 frames of 288 x 384 -> fp32 [64, 3, 16, 224, 224]) as ONE lv_clip_transform launch, sources resident in HBM; `e2e` adds
+    the H2D copy of the pinned uint8 frames and the crop-box table.  Algorithmic bytes per clip: 3*T*S*S*4 written + the crop box
+    (<= T*H*W*3 source bytes) read once.  `cpu_baseline`: the reference's own chain (lavila Permute + torchvision + NormalizeVideo,
+    baseline/_ref when installed) on ONE host core -- the reference spends 10 DataLoader workers per GPU on it."""
+    import time as _t
+    import torch
+    from lavila_b200.data import GpuClipTransform
+    H, W = src_hw
+    g = torch.Generator().manual_seed(0)
+    src_h = torch.randint(0, 256, (batch, frames, H, W, 3), generator=g, dtype=torch.uint8).pin_memory()
+    src_d = src_h.to(dev)
+    tf = GpuClipTransform(crop, "train", device=dev)
+    torch.manual_seed(0)
+    tf(src_d)
+    boxes = list(tf.last_boxes)
+    box_bytes = sum(b[2] * b[3] for b in boxes) * 3 * frames
+    out_bytes = batch * 3 * frames * crop * crop * 4
+    flush = torch.empty(256 * 2 ** 20, dtype=torch.uint8, device=dev)          # > the 126 MB L2
+    ms = []
+    for _ in range(6):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        tf(src_d, boxes=boxes)
+        e1.record()
+        torch.cuda.synchronize()
+        ms.append(e0.elapsed_time(e1))
+    k_ms = sorted(ms[1:])[len(ms[1:]) // 2]
+    t0 = _t.time()
+    for _ in range(3):
+        out = tf(src_h, boxes=boxes)
+        float(out[0, 0, 0, 0, 0])
+    e2e_s = (_t.time() - t0) / 3
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        peaks = {}
+    peak = float(peaks.get("hbm_gbs", 7700.0))
+    res = {"workload": "train transform (RandomResizedCrop scale 0.5-1 + NormalizeVideo), %d clips x %d uint8 frames %dx%d -> %d^2 fp32"
+                       % (batch, frames, H, W, crop),
+           "value": round(batch / (k_ms / 1e3), 1), "unit": "clips/s", "kernel_ms": round(k_ms, 3), "gpu_launches": 1,
+           "roofline": {"bound": "hbm", "achieved": round((box_bytes + out_bytes) / k_ms / 1e6, 1), "peak": peak, "unit": "GB/s",
+                        "frac": round((box_bytes + out_bytes) / k_ms / 1e6 / peak, 3), "bytes_read": box_bytes,
+                        "bytes_written": out_bytes, "l2": "256 MB flushed between launches"},
+           "e2e": {"value": round(batch / e2e_s, 1), "unit": "clips/s", "h2d_bytes_per_step": src_h.numel() + batch * 96,
+                   "d2h_bytes_per_step": 4}}
+    # CPU: the reference's chain, one clip at a time like a DataLoader worker, on one core
+    try:
+        from baseline import ref_shim
+        ref_ok = ref_shim.install()
+    except Exception:
+        ref_ok = False
+    try:
+        from torchvision import transforms
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            from torchvision.transforms import _transforms_video as tvv
+        if ref_ok:
+            from lavila.data.video_transforms import Permute
+        else:
+            from lavila_b200.data import Permute
+        from lavila_b200.data import video_transforms as VT
+        chain = transforms.Compose([Permute([3, 0, 1, 2]), transforms.RandomResizedCrop(crop, scale=(0.5, 1.0), antialias=False),
+                                    tvv.NormalizeVideo(mean=list(VT.OPENAI_MEAN), std=list(VT.OPENAI_STD))])
+        nthr = torch.get_num_threads()
+        torch.set_num_threads(1)
+        n, t0 = 0, _t.time()
+        while _t.time() - t0 < cpu_budget_s and n < batch:
+            chain(src_h[n].float())           # video_loader hands over fp32 frames (datasets.py:74-75)
+            n += 1
+        dt = _t.time() - t0
+        torch.set_num_threads(nthr)
+        res["cpu_baseline"] = {"value": round(n / dt, 2), "unit": "clips/s", "cores": 1, "kind": "reference" if ref_ok else "port",
+                               "sample": "%d clips of the same batch, lavila Permute + torchvision %s RandomResizedCrop(antialias=False) "
+                                         "+ NormalizeVideo, fp32 frames" % (n, __import__("torchvision").__version__)}
+    except Exception as e:
+        res["cpu_baseline"] = {"error": repr(e)[:200]}
+    return res
 
 
 def block_roofline(step_fn, engine, torch, B, frames, flop_kw):

@@ -268,6 +268,24 @@ int lv_ssl_clip_loss_bwd(const float* img, const float* txt, const float* scale_
  * ---------------------------------------------------------------------------------------------- */
 int lv_top_p_filter(float* logits, int64_t ld, int rows, int V, float temperature, float top_p, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Input pipeline: decoded frames -> normalised clip, a batch per launch.  Replaces the CPU transform chain of the DataLoader
+ * workers: main_pretrain.py:263-272 (train: Permute, RandomResizedCrop, NormalizeVideo), :274-281 (val: Permute, Resize,
+ * CenterCrop, NormalizeVideo), lavila/data/video_transforms.py:15-32.  The random crop box is drawn on the host
+ * (lavila_b200/data/video_transforms.py restates torchvision's get_params with the same RNG calls).
+ *   desc      device table, 12 x int64 per clip: { src pointer (frames x H x W x 3, channel-interleaved, as the decoder returns
+ *             them: lavila/data/datasets.py:25-75), H, W, box_i, box_j, box_h, box_w (source rectangle, inside the frame),
+ *             RH, RW (size the rectangle is resized to), off_y, off_x (top-left of the output window in the resized image:
+ *             off + OH <= RH, off + OW <= RW), frame_stride (elements between frames, >= H*W*3) }
+ *   src_dtype 0 = uint8, 1 = fp32 (the reference converts to fp32 before transforming; values are the same 0..255)
+ *   antialias 0 = plain bilinear, align_corners = False (torchvision 0.11.2 on tensors, the reference's pinned version);
+ *             1 = antialiased bilinear (torchvision >= 0.17 default)
+ *   mean, std HOST pointers to 3 floats (per channel, in 0..255 units as in main_pretrain.py:268-270)
+ *   out       fp32 [clips][3][frames][OH][OW] = (resized - mean) / std, the layout SpaceTimeTransformer.forward takes
+ * ---------------------------------------------------------------------------------------------- */
+int lv_clip_transform(const int64_t* desc, int clips, int frames, int src_dtype, int antialias, const float* mean,
+                      const float* std, float* out, int OH, int OW, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -39,6 +39,7 @@ SIGNATURES = {
     "lv_clip_loss_fwd_gather": [P, P, P, I, I, I, ctypes.c_uint32, P, P, P, I, P, P, P, P, P, L, P],
     "lv_clip_loss_gather_max_rows": [I],
     "lv_top_p_filter": [P, L, I, I, F, F, P],
+    "lv_clip_transform": [P, I, I, I, I, P, P, P, I, I, P],
     "lv_ssl_clip_loss_fwd": [P, P, P, P, P, I, I, P, P, P, P, P, P],
     "lv_ssl_clip_loss_bwd": [P, P, P, P, P, P, P, P, F, F, I, I, I, I, P, P, P, P],
 }

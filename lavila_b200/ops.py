@@ -366,3 +366,18 @@ def top_p_filter_(logits, temperature, top_p):
     rc = L.lib().lv_top_p_filter(logits.data_ptr(), logits.stride(0), rows, V, float(temperature), float(top_p), _stream())
     L.check(rc, "lv_top_p_filter")
     return logits
+
+
+def clip_transform(desc, sources, frames, antialias, mean, std, out):
+    """out[B,3,T,OH,OW] = normalise(resize(crop(frames))) for a batch of clips (lv_clip_transform); `desc` is the device table of
+    12 int64 per clip, `sources` the frame tensors it points at (kept alive by the caller; only their dtype is read here)."""
+    _check_cuda(desc, out, *sources)
+    if out.dtype != F32 or not out.is_contiguous() or desc.dtype != torch.int64 or not desc.is_contiguous():
+        raise L.LavilaB200Error("clip_transform: out must be contiguous fp32, desc contiguous int64")
+    B, _, T, OH, OW = out.shape
+    m = (ctypes.c_float * 3)(*mean)
+    s = (ctypes.c_float * 3)(*std)
+    rc = L.lib().lv_clip_transform(desc.data_ptr(), B, T, 0 if sources[0].dtype == torch.uint8 else 1, int(bool(antialias)), m, s,
+                                   out.data_ptr(), OH, OW, _stream())
+    L.check(rc, "lv_clip_transform")
+    return out

@@ -423,7 +423,7 @@ DOUBLES = ("gemm", "wgrad_splits", "layernorm_fwd", "layernorm_bwd", "group_attn
            "cls_attn_bwd", "cls_kv_finalize", "cls_query_attn_fwd", "cls_query_attn_bwd", "add_rows", "cast_bf16", "colsum_bf16",
            "patch_im2col", "embed_assemble", "embed_assemble_bwd", "text_embed", "text_embed_bwd", "argmax_i64", "gather_rows",
            "l2norm_fwd", "l2norm_bwd", "clip_loss_fwd", "clip_loss_bwd", "flash_attn_fwd", "flash_attn_fwd_dyn", "gemm_skinny",
-           "ssl_clip_loss_fwd", "ssl_clip_loss_bwd", "top_p_filter_",
+           "ssl_clip_loss_fwd", "ssl_clip_loss_bwd", "top_p_filter_", "clip_transform",
            "space_attn_cls_fused_supported", "space_attn_fwd_cls", "space_attn_bwd_cls",
            "time_attn_cls_fused_supported", "time_attn_fwd_cls", "time_attn_bwd_cls")
 
@@ -436,6 +436,20 @@ def top_p_filter_(logits, temperature, top_p):
     rm[..., -1:] = False
     logits.copy_(x.masked_fill(rm.scatter(1, idx, rm), float("-inf")))
     return logits
+
+
+def clip_transform(desc, sources, frames, antialias, mean, std, out):
+    """lv_clip_transform's contract (include/lavila_b200.h) row by row of the descriptor table: source rectangle -> bilinear resize
+    to RH x RW (taps clamped to the rectangle) -> OH x OW window at (off_y, off_x) -> (v - mean) / std, channels first."""
+    OH, OW = out.shape[-2:]
+    m = torch.tensor(mean, dtype=torch.float32).view(3, 1, 1, 1)
+    s = torch.tensor(std, dtype=torch.float32).view(3, 1, 1, 1)
+    for b, src in enumerate(sources):
+        _, H, W, i, j, h, w, RH, RW, oy, ox, _ = (int(v) for v in desc[b].tolist())
+        box = src[:frames, i:i + h, j:j + w, :].permute(0, 3, 1, 2).float()                     # T x 3 x h x w
+        r = torch.nn.functional.interpolate(box, size=(RH, RW), mode="bilinear", align_corners=False, antialias=bool(antialias))
+        out[b].copy_(((r[:, :, oy:oy + OH, ox:ox + OW].permute(1, 0, 2, 3) - m) / s).to(out.device))
+    return out
 
 
 def space_attn_cls_fused_supported(n):
