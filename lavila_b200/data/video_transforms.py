@@ -92,6 +92,16 @@ class GpuClipTransform:
         return 0, 0, height, width, rh, rw, oy, ox
 
     def __call__(self, clips, boxes=None):
+        return self.run(*self.prepare(clips, boxes))
+
+    def run(self, desc, sources, frames):
+        """The launch alone: descriptor table (device) + the frame tensors it points at -> the normalised batch."""
+        out = torch.empty(len(sources), 3, frames, self.crop_size, self.crop_size, dtype=torch.float32, device=self.device)
+        ops.clip_transform(desc, sources, frames, self.antialias, self.mean, self.std, out)
+        return out
+
+    def prepare(self, clips, boxes=None):
+        """Host side of a batch: draw / check the geometry of every clip, move the frames to the device, upload the table."""
         if torch.is_tensor(clips):
             if clips.dim() != 5:
                 raise ValueError("expected B x T x H x W x 3")
@@ -121,10 +131,7 @@ class GpuClipTransform:
         desc = torch.tensor(rows, dtype=torch.int64)
         if self.device.type == "cuda":
             desc = desc.pin_memory()
-        desc = desc.to(self.device, non_blocking=True)
-        out = torch.empty(len(clips), 3, T, self.crop_size, self.crop_size, dtype=torch.float32, device=self.device)
-        ops.clip_transform(desc, keep, T, self.antialias, self.mean, self.std, out)
-        return out
+        return desc.to(self.device, non_blocking=True), keep, T
 
 
 def transforms_for_model(model_name, is_training, device="cuda", antialias=False):
