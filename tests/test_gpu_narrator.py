@@ -198,7 +198,10 @@ def test_flash_attention(B, H, Lq, Lk, mqa, causal):
 
 
 @pytest.mark.parametrize("M,N,K,flags", [(32, 1600, 1600, "bias"), (5, 4800, 1600, "bias"), (320, 6400, 1600, "gelu"),
-                                         (32, 1600, 6400, "resid_gate"), (70, 768, 768, "sqrelu"), (32, 1600, 1600, "resid")])
+                                         (32, 1600, 6400, "resid_gate"), (70, 768, 768, "sqrelu"), (32, 1600, 1600, "resid"),
+                                         # several 64-row blocks of sequences (num_return_sequences > 2 at batch 32), ragged last block
+                                         (128, 1600, 1600, "bias"), (320, 1600, 6400, "resid_gate"), (512, 4800, 1600, "bias"),
+                                         (100, 768, 768, "sqrelu"), (68, 1600, 1600, "resid"), (320, 6400, 1600, "bias")])
 def test_skinny_gemm(M, N, K, flags):
     """lv_gemm_skinny_bf16 (decode-sized GEMMs, csrc/gemm_skinny.cu) against fp32 torch on the same bf16 operands, every epilogue
     the gated GPT-2 uses; two runs are bit-identical (deterministic split-K)."""
