@@ -143,7 +143,31 @@ def side_join(dev):
     st["dirty"] = False
 
 
+# fp32 gradient buffers of one autograd node come out of ONE zero-filled allocation (a fill launch per node instead of one per
+# parameter: 18 per SpaceTimeBlock); each is a contiguous, 256-byte aligned view, so the split-K atomics and DDP see ordinary tensors.
+_GRAD_POOL = []
+
+
+@contextlib.contextmanager
+def grad_pool(params):
+    params = [p for p in params if p is not None]
+    total = sum((p.numel() + 63) // 64 * 64 for p in params)
+    pool = {"buf": torch.zeros(total, device=params[0].device, dtype=F32) if params else None, "off": 0}
+    _GRAD_POOL.append(pool)
+    try:
+        yield
+    finally:
+        _GRAD_POOL.pop()
+
+
 def _zeros_like_param(p):
+    if _GRAD_POOL:
+        pool = _GRAD_POOL[-1]
+        n = p.numel()
+        if pool["buf"] is not None and pool["buf"].device == p.device and pool["off"] + n <= pool["buf"].numel():
+            v = pool["buf"][pool["off"]:pool["off"] + n].view(p.shape)
+            pool["off"] += (n + 63) // 64 * 64
+            return v
     return torch.zeros(p.shape, device=p.device, dtype=F32)
 
 
@@ -354,12 +378,13 @@ class SpaceTimeBlockFn(torch.autograd.Function):
         B, N, D = ctx.shape
         dy = dy.contiguous().view(B * N, D)
         dy_b = take_bf16(dy)
-        dr, dr_b, g_m = mlp_sub_bwd(dy, dy_b, _mlp_params(ps), s_m)
-        del dy_b
-        dxt, dxt_b, g_s = attn_sub_bwd(dr, dr_b, _attn_params(ps, "norm1", "attn"), s_s)
-        del dr_b
-        # x feeds norm3 (LN), the time residual (grad dxt) and the space residual (grad dr)
-        dx, dx_b, g_t = attn_sub_bwd(dxt, dxt_b, _attn_params(ps, "norm3", "timeattn"), s_t, adds=(dr, dxt))
+        with grad_pool([ps[k] for k in BLOCK_PARAM_ORDER]):
+            dr, dr_b, g_m = mlp_sub_bwd(dy, dy_b, _mlp_params(ps), s_m)
+            del dy_b
+            dxt, dxt_b, g_s = attn_sub_bwd(dr, dr_b, _attn_params(ps, "norm1", "attn"), s_s)
+            del dr_b
+            # x feeds norm3 (LN), the time residual (grad dxt) and the space residual (grad dr)
+            dx, dx_b, g_t = attn_sub_bwd(dxt, dxt_b, _attn_params(ps, "norm3", "timeattn"), s_t, adds=(dr, dxt))
         stash_bf16(dx, dx_b)
         grads = {
             "norm3.weight": g_t["ln_w"], "norm3.bias": g_t["ln_b"], "timeattn.qkv.weight": g_t["qkv_w"],
@@ -503,8 +528,9 @@ class TextBlockFn(torch.autograd.Function):
         B, Lc, W = ctx.shape
         dy = dy.contiguous().view(B * Lc, W)
         dy_b = take_bf16(dy)
-        dx1, dx1_b, g_m = mlp_sub_bwd(dy, dy_b, _mlp_params(ps, "ln_2", "mlp.c_fc", "mlp.c_proj"), s_m)
-        dx, dx_b, g_a = attn_sub_bwd(dx1, dx1_b, _text_attn_params(ps), s_a, adds=(dx1,))
+        with grad_pool([ps[k] for k in TEXT_PARAM_ORDER]):
+            dx1, dx1_b, g_m = mlp_sub_bwd(dy, dy_b, _mlp_params(ps, "ln_2", "mlp.c_fc", "mlp.c_proj"), s_m)
+            dx, dx_b, g_a = attn_sub_bwd(dx1, dx1_b, _text_attn_params(ps), s_a, adds=(dx1,))
         stash_bf16(dx, dx_b)
         grads = {
             "ln_1.weight": g_a["ln_w"], "ln_1.bias": g_a["ln_b"], "attn.in_proj_weight": g_a["qkv_w"],
