@@ -135,3 +135,22 @@ def test_bench_reference_arm_contract():
     assert d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"]
+
+
+def test_grad_pool_hands_out_aligned_zero_views_and_falls_back():
+    """engine.grad_pool: the fp32 gradient buffers of one autograd node are views of ONE zero-filled allocation (64-float = 256-byte
+    aligned, contiguous, the parameter's shape); requests beyond the pool (or outside one) get their own torch.zeros."""
+    from lavila_b200 import engine
+    ps = [torch.nn.Parameter(torch.randn(5, 7)), torch.nn.Parameter(torch.randn(3)), torch.nn.Parameter(torch.randn(70, 2))]
+    with engine.grad_pool(ps):
+        gs = [engine._zeros_like_param(p) for p in ps]
+        extra = engine._zeros_like_param(torch.nn.Parameter(torch.randn(1000)))          # does not fit any more
+    base = gs[0].untyped_storage().data_ptr()
+    for g, p in zip(gs, ps):
+        assert g.shape == p.shape and g.dtype == torch.float32 and g.is_contiguous() and float(g.abs().sum()) == 0.0
+        assert g.untyped_storage().data_ptr() == base and (g.data_ptr() - base) % 256 == 0
+    assert extra.untyped_storage().data_ptr() != base and extra.shape == (1000,)
+    gs[0].add_(1.0)
+    assert float(gs[1].abs().sum()) == 0.0 and float(gs[2].abs().sum()) == 0.0            # disjoint slices
+    lone = engine._zeros_like_param(ps[0])                                               # outside a pool
+    assert lone.untyped_storage().data_ptr() != base and not engine._GRAD_POOL
